@@ -1,0 +1,201 @@
+// capi.cu — the extern "C" surface declared in include/envgs_b200.h.
+#include <stdarg.h>
+#include <atomic>
+#include <mutex>
+#include <string.h>
+#include "lbvh.cuh"
+#include "raster_state.cuh"
+
+namespace envgs {
+
+static thread_local char g_error[1024] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+int raster_forward_dispatch(const envgs_raster_args& a, const envgs_raster_out& o, envgs_alloc_fn ga, envgs_alloc_fn ba,
+                            envgs_alloc_fn ia, void* user, cudaStream_t stream);
+int raster_backward_dispatch(const envgs_raster_args& a, const int* radii, int R, void* geom, void* binning, void* img,
+                             const envgs_raster_grads& gr, cudaStream_t stream);
+int mark_visible_impl(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t stream);
+int trace_forward_impl(Lbvh& bvh, unsigned int* counter, const envgs_trace_args& a, const envgs_trace_out& o, cudaStream_t stream);
+int trace_backward_impl(Lbvh& bvh, unsigned int* counter, const envgs_trace_args& a, const envgs_trace_grads& g, cudaStream_t stream);
+
+}  // namespace envgs
+
+struct envgs_tracer {
+    envgs::Lbvh bvh;
+    unsigned int* counter = nullptr;
+};
+
+using namespace envgs;
+
+extern "C" {
+
+const char* envgs_last_error(void) { return g_error; }
+int envgs_version(void) { return 100; }
+uint64_t envgs_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+static int check_raster_args(const envgs_raster_args* a) {
+    if (!a) { set_error("args is NULL"); return ENVGS_ERR_INVALID; }
+    if (a->P < 0 || a->width <= 0 || a->height <= 0) { set_error("bad sizes P=%d W=%d H=%d", a->P, a->width, a->height); return ENVGS_ERR_INVALID; }
+    if (a->width > 32000 || a->height > 32000) { set_error("image larger than 32000 px is not supported"); return ENVGS_ERR_INVALID; }
+    if (a->C != 3 && a->C != 5 && a->C != 7) { set_error("unsupported channel count C=%d (3, 5 or 7)", a->C); return ENVGS_ERR_INVALID; }
+    if (a->P == 0) return ENVGS_OK;
+    if (!a->means3D || !a->opacities || !a->background || !a->viewmatrix || !a->projmatrix || !a->campos) {
+        set_error("a required pointer (means3D/opacities/background/viewmatrix/projmatrix/campos) is NULL");
+        return ENVGS_ERR_INVALID;
+    }
+    if (a->colors_precomp == nullptr) {
+        if (a->C != 3) { set_error("For non-RGB, provide precomputed Gaussian colors!"); return ENVGS_ERR_INVALID; }   // rasterizer_impl.cu:244-247
+        if (a->shs == nullptr) { set_error("either shs or colors_precomp must be given"); return ENVGS_ERR_INVALID; }
+        if (a->sh_degree < 0 || a->sh_degree > 3 || (a->sh_degree + 1) * (a->sh_degree + 1) > a->sh_coeffs) {
+            set_error("sh_degree %d does not fit %d coefficients", a->sh_degree, a->sh_coeffs);
+            return ENVGS_ERR_INVALID;
+        }
+    }
+    if (a->transMat_precomp == nullptr && (a->scales == nullptr || a->rotations == nullptr)) {
+        set_error("either scales+rotations or transMat_precomp must be given");
+        return ENVGS_ERR_INVALID;
+    }
+    return ENVGS_OK;
+}
+
+int envgs_raster_forward(const envgs_raster_args* args, const envgs_raster_out* out, envgs_alloc_fn geom_alloc,
+                         envgs_alloc_fn binning_alloc, envgs_alloc_fn img_alloc, void* alloc_user, void* stream) {
+    int rc = check_raster_args(args);
+    if (rc != ENVGS_OK) return rc;
+    if (!out || !out->out_color || !out->out_others || !out->out_weight) { set_error("output pointer is NULL"); return ENVGS_ERR_INVALID; }
+    if (!geom_alloc || !binning_alloc || !img_alloc) { set_error("allocator callback is NULL"); return ENVGS_ERR_INVALID; }
+    if (args->P == 0) return 0;   // reference leaves the zero-filled outputs untouched (rasterize_points.cu:100)
+    return raster_forward_dispatch(*args, *out, geom_alloc, binning_alloc, img_alloc, alloc_user, (cudaStream_t)stream);
+}
+
+int envgs_raster_backward(const envgs_raster_args* args, const int32_t* radii, int32_t num_rendered, void* geom_buffer,
+                          void* binning_buffer, void* img_buffer, const envgs_raster_grads* grads, void* stream) {
+    int rc = check_raster_args(args);
+    if (rc != ENVGS_OK) return rc;
+    if (args->P == 0) return ENVGS_OK;
+    if (!grads || !geom_buffer || !img_buffer || (num_rendered > 0 && !binning_buffer)) { set_error("buffer pointer is NULL"); return ENVGS_ERR_INVALID; }
+    if (!grads->dL_dout_color || !grads->dL_dout_others || !grads->dL_dmeans2D || !grads->dL_dcolors || !grads->dL_dopacity ||
+        !grads->dL_dmeans3D || !grads->dL_dtransMat || !grads->dL_dscales || !grads->dL_drotations || !grads->dL_dnormal) {
+        set_error("gradient pointer is NULL");
+        return ENVGS_ERR_INVALID;
+    }
+    if (args->shs && !grads->dL_dsh) { set_error("dL_dsh is NULL although shs were given"); return ENVGS_ERR_INVALID; }
+    return raster_backward_dispatch(*args, radii, num_rendered, geom_buffer, binning_buffer, img_buffer, *grads, (cudaStream_t)stream);
+}
+
+int envgs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix, uint8_t* present,
+                       void* stream) {
+    (void)projmatrix;
+    if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) { set_error("bad arguments to envgs_mark_visible"); return ENVGS_ERR_INVALID; }
+    return mark_visible_impl(P, means3D, viewmatrix, present, (cudaStream_t)stream);
+}
+
+size_t envgs_raster_geom_bytes(int32_t P) { return GeomState::carve(nullptr, P, nullptr, scan_temp_bytes(P)); }
+size_t envgs_raster_img_bytes(int32_t width, int32_t height) { return ImageState::carve(nullptr, width, height, nullptr); }
+size_t envgs_raster_binning_bytes(int32_t n) { return BinningState::carve(nullptr, n, nullptr, sort_temp_bytes(n)); }
+
+envgs_tracer* envgs_tracer_create(void) {
+    envgs_tracer* h = new (std::nothrow) envgs_tracer();
+    if (!h) { set_error("out of host memory"); return nullptr; }
+    if (cudaMalloc(&h->counter, 256) != cudaSuccess) {
+        set_error("cudaMalloc failed for the tracer work counter: %s", cudaGetErrorString(cudaGetLastError()));
+        delete h;
+        return nullptr;
+    }
+    return h;
+}
+
+void envgs_tracer_destroy(envgs_tracer* h) {
+    if (!h) return;
+    if (h->bvh.owns_storage && h->bvh.storage) cudaFree(h->bvh.storage);
+    if (h->counter) cudaFree(h->counter);
+    delete h;
+}
+
+size_t envgs_tracer_bvh_bytes(int32_t P) { return lbvh_storage_bytes(P); }
+
+int envgs_tracer_build(envgs_tracer* h, const float* vertices, int32_t num_vertices, int32_t rebuild, envgs_alloc_fn alloc,
+                       void* alloc_user, void* stream) {
+    if (!h) { set_error("tracer handle is NULL"); return ENVGS_ERR_INVALID; }
+    if (num_vertices < 0 || num_vertices % 4 != 0) { set_error("vertices must hold 4 corners per surfel (got %d)", num_vertices); return ENVGS_ERR_INVALID; }
+    const int P = num_vertices / 4;
+    if (P > 0 && !vertices) { set_error("vertices is NULL"); return ENVGS_ERR_INVALID; }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (P > h->bvh.capacity) {
+        int cap = P + P / 8;   // head-room so densification does not reallocate every step
+        size_t bytes = lbvh_storage_bytes(cap);
+        char* mem = nullptr;
+        if (alloc) {
+            mem = (char*)alloc(alloc_user, bytes);
+            if (!mem) { set_error("BVH allocator returned NULL for %zu bytes", bytes); return ENVGS_ERR_ALLOC; }
+            if (h->bvh.owns_storage && h->bvh.storage) cudaFree(h->bvh.storage);
+            h->bvh.owns_storage = false;
+        } else {
+            ENVGS_CUDA_TRY(cudaStreamSynchronize(s));
+            if (h->bvh.owns_storage && h->bvh.storage) cudaFree(h->bvh.storage);
+            ENVGS_CUDA_TRY(cudaMalloc(&mem, bytes));
+            h->bvh.owns_storage = true;
+        }
+        h->bvh.storage = mem;
+        h->bvh.capacity = cap;
+        h->bvh.P = 0;
+        rebuild = 1;
+    }
+    if (P > 0) lbvh_carve(h->bvh, h->bvh.storage, h->bvh.capacity);
+    return lbvh_build(h->bvh, vertices, P, rebuild != 0, s);
+}
+
+static int check_trace_args(envgs_tracer* h, const envgs_trace_args* a) {
+    if (!h) { set_error("tracer handle is NULL"); return ENVGS_ERR_INVALID; }
+    if (!a) { set_error("args is NULL"); return ENVGS_ERR_INVALID; }
+    if (a->H <= 0 || a->W <= 0) { set_error("bad ray grid %dx%d", a->H, a->W); return ENVGS_ERR_INVALID; }
+    if (h->bvh.P != a->P || a->P <= 0) {
+        set_error("acceleration structure holds %d surfels but %d were passed; call build_acceleration_structure first", h->bvh.P, a->P);
+        return ENVGS_ERR_STATE;
+    }
+    if (a->max_trace_depth < 0 || a->max_trace_depth > TR_MAX_TRACE_DEPTH) { set_error("max_trace_depth must be 0..%d", TR_MAX_TRACE_DEPTH); return ENVGS_ERR_INVALID; }
+    if (!a->ray_o || !a->ray_d || !a->background || !a->means3D || !a->opacities || !a->scales || !a->rotations || !a->campos ||
+        !a->viewmatrix || !a->projmatrix) { set_error("a required tracer pointer is NULL"); return ENVGS_ERR_INVALID; }
+    if ((a->shs == nullptr) == (a->colors_precomp == nullptr)) { set_error("provide exactly one of shs / colors_precomp"); return ENVGS_ERR_INVALID; }
+    if (a->shs && (a->sh_degree < 0 || a->sh_degree > 3 || (a->sh_degree + 1) * (a->sh_degree + 1) > a->sh_coeffs)) {
+        set_error("sh_degree %d does not fit %d coefficients", a->sh_degree, a->sh_coeffs);
+        return ENVGS_ERR_INVALID;
+    }
+    return ENVGS_OK;
+}
+
+int envgs_trace_forward(envgs_tracer* h, const envgs_trace_args* args, const envgs_trace_out* out, void* stream) {
+    int rc = check_trace_args(h, args);
+    if (rc != ENVGS_OK) return rc;
+    if (!out || !out->out_rgb || !out->out_dpt || !out->out_acc || !out->out_norm || !out->out_dist || !out->out_aux || !out->mid_val) {
+        set_error("tracer output pointer is NULL");
+        return ENVGS_ERR_INVALID;
+    }
+    if (args->training && !out->a_weights) { set_error("a_weights is NULL although training is set"); return ENVGS_ERR_INVALID; }
+    return trace_forward_impl(h->bvh, h->counter, *args, *out, (cudaStream_t)stream);
+}
+
+int envgs_trace_backward(envgs_tracer* h, const envgs_trace_args* args, const envgs_trace_grads* g, void* stream) {
+    int rc = check_trace_args(h, args);
+    if (rc != ENVGS_OK) return rc;
+    if (!g || !g->out_rgb || !g->out_dpt || !g->out_acc || !g->out_norm || !g->out_aux || !g->mid_val || !g->dL_drgb || !g->dL_ddpt ||
+        !g->dL_dacc || !g->dL_dnorm || !g->dL_daux || !g->dL_dray_o || !g->dL_dray_d || !g->dL_dmeans3D || !g->dL_dcolors ||
+        !g->dL_dopacities || !g->dL_dscales || !g->dL_drotations) {
+        set_error("tracer gradient pointer is NULL");
+        return ENVGS_ERR_INVALID;
+    }
+    if (args->shs && !g->dL_dshs) { set_error("dL_dshs is NULL although shs were given"); return ENVGS_ERR_INVALID; }
+    if (args->others_precomp && !g->dL_dothers) { set_error("dL_dothers is NULL although others_precomp was given"); return ENVGS_ERR_INVALID; }
+    return trace_backward_impl(h->bvh, h->counter, *args, *g, (cudaStream_t)stream);
+}
+
+}  // extern "C"

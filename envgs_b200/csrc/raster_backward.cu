@@ -1,0 +1,425 @@
+// raster_backward.cu — backward pass of the surfel rasterizer for sm_100a.
+//
+//   render_bwd_kernel      per tile, back-to-front re-walk of the instance list (RAST5/cuda_rasterizer/backward.cu:143-440).
+//                          Per-(pixel,surfel) partial gradients are reduced warp -> CTA (shared memory) -> one
+//                          global atomic per (tile, surfel, component) instead of the reference's per-pixel atomics.
+//   preprocess_bwd_kernel  per surfel chain rule dL/dT, dL/dnormal, dL/dmean2D -> mean/scale/quat (+SH)
+//                          (backward.cu:443-630), including the densification-signal overwrite (:626-629).
+#include "raster_state.cuh"
+
+namespace envgs {
+
+constexpr int BB = 128;          // surfels staged per batch (CTA = 256 threads; keeps static smem < 48 KB for C = 7)
+constexpr int NG_FIX = 15;       // reduced values besides colour: normal(3) opacity(1) dT(9) dmean2D(2)
+
+template <int C>
+__global__ void __launch_bounds__(256) render_bwd_kernel(
+    const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int tiles_x,
+    const float* __restrict__ bg, const float4* __restrict__ rec, const short4* __restrict__ pixbox,
+    const float* __restrict__ features, const float* __restrict__ final_Ts, const uint32_t* __restrict__ n_contrib,
+    const float* __restrict__ dL_dpixels, const float* __restrict__ dL_dothers, float* __restrict__ dL_dtransMat,
+    float* __restrict__ dL_dmean2D, float* __restrict__ dL_dnormal3D, float* __restrict__ dL_dopacity,
+    float* __restrict__ dL_dcolors) {
+    constexpr int NG = C + NG_FIX;   // per-surfel reduced values: [0,C) colour, C..C+2 normal, C+3 opacity, C+4..C+12 dT, C+13,C+14 dmean2D
+    __shared__ float4 s_r0[BB], s_r1[BB], s_r2[BB], s_r3[BB];
+    __shared__ short4 s_box[BB];
+    __shared__ int s_id[BB];
+    __shared__ float s_feat[BB * C];
+    __shared__ float s_g[BB * NG];
+    __shared__ uint32_t s_max;
+
+    const int tile = blockIdx.x;
+    const int tx = tile % tiles_x, ty = tile / tiles_x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wx0 = tx * TILE_X + (warp & 1) * 8, wy0 = ty * TILE_Y + (warp >> 1) * 4;
+    const int wx1 = wx0 + 7, wy1 = wy0 + 3;
+    const int pix_x = wx0 + (lane & 7), pix_y = wy0 + (lane >> 3);
+    const bool inside = pix_x < W && pix_y < H;
+    const size_t HW = (size_t)W * H;
+    const size_t pix_id = (size_t)W * pix_y + pix_x;
+    const float pxf = (float)pix_x, pyf = (float)pix_y;
+    const uint2 range = ranges[tile];
+
+    const float T_final = inside ? final_Ts[pix_id] : 0.0f;
+    float T = T_final;
+    const uint32_t last_contributor = inside ? n_contrib[pix_id] : 0u;
+    const uint32_t median_contributor = inside ? n_contrib[pix_id + HW] : 0u;
+
+    if (tid == 0) s_max = 0;
+    __syncthreads();
+    {
+        uint32_t m = __reduce_max_sync(0xffffffffu, last_contributor);
+        if (lane == 0) atomicMax(&s_max, m);
+    }
+    for (int k = tid; k < BB * NG; k += 256) s_g[k] = 0.0f;
+    __syncthreads();
+    const int total = (int)s_max;   // entries beyond the tile-wide last contributor are never visited
+    if (total == 0) return;
+    const uint32_t warp_last = __reduce_max_sync(0xffffffffu, last_contributor);
+
+    float accum_rec[C], dL_dpixel[C], last_color[C];
+#pragma unroll
+    for (int ch = 0; ch < C; ch++) { accum_rec[ch] = 0; last_color[ch] = 0; dL_dpixel[ch] = 0; }
+    float dL_dreg = 0, dL_ddepth = 0, dL_daccum = 0, dL_dn0 = 0, dL_dn1 = 0, dL_dn2 = 0, dL_dmedian_depth = 0;
+    if (inside) {
+#pragma unroll
+        for (int ch = 0; ch < C; ch++) dL_dpixel[ch] = dL_dpixels[ch * HW + pix_id];
+        dL_ddepth = dL_dothers[DEPTH_OFFSET * HW + pix_id];
+        dL_daccum = dL_dothers[ALPHA_OFFSET * HW + pix_id];
+        dL_dreg = dL_dothers[DISTORTION_OFFSET * HW + pix_id];
+        dL_dn0 = dL_dothers[(NORMAL_OFFSET + 0) * HW + pix_id];
+        dL_dn1 = dL_dothers[(NORMAL_OFFSET + 1) * HW + pix_id];
+        dL_dn2 = dL_dothers[(NORMAL_OFFSET + 2) * HW + pix_id];
+        dL_dmedian_depth = dL_dothers[MIDDEPTH_OFFSET * HW + pix_id];
+    }
+    float bg_dot_dpixel = 0.0f;
+#pragma unroll
+    for (int ch = 0; ch < C; ch++) bg_dot_dpixel += bg[ch] * dL_dpixel[ch];
+
+    float last_depth = 0, accum_depth_rec = 0, accum_alpha_rec = 0, last_alpha = 0, last_dL_dT = 0;
+    float ln0 = 0, ln1 = 0, ln2 = 0, an0 = 0, an1 = 0, an2 = 0;
+    const float final_D = inside ? final_Ts[pix_id + HW] : 0.0f;
+    const float final_D2 = inside ? final_Ts[pix_id + 2 * HW] : 0.0f;
+    const float final_A = 1.0f - T_final;
+
+    const int rounds = (total + BB - 1) / BB;
+    for (int i = 0; i < rounds; i++) {
+        // positions are 1-based; this batch covers pos = total - i*BB - t, t = 0..nb-1 (descending)
+        const int nb = min(BB, total - i * BB);
+        if (tid < nb) {
+            int pos = total - i * BB - tid;
+            int id = (int)point_list[range.x + pos - 1];
+            s_id[tid] = id;
+            s_r0[tid] = rec[4 * (size_t)id + 0];
+            s_r1[tid] = rec[4 * (size_t)id + 1];
+            s_r2[tid] = rec[4 * (size_t)id + 2];
+            s_r3[tid] = rec[4 * (size_t)id + 3];
+            s_box[tid] = pixbox[id];
+#pragma unroll
+            for (int ch = 0; ch < C; ch++) s_feat[ch * BB + tid] = features[(size_t)id * C + ch];
+        }
+        __syncthreads();
+
+        for (int j = 0; j < nb; j++) {
+            const uint32_t pos = (uint32_t)(total - i * BB - j);
+            if (pos > warp_last) continue;                                           // warp-uniform
+            const short4 bb = s_box[j];
+            if (bb.x > wx1 || bb.z < wx0 || bb.y > wy1 || bb.w < wy0) continue;   // warp-uniform
+            const float4 r0 = s_r0[j], r1 = s_r1[j], r2 = s_r2[j];
+            const float3 Tu = f3(r0.x, r0.y, r0.z), Tv = f3(r0.w, r1.x, r1.y), Tw = f3(r1.z, r1.w, r2.x);
+
+            float g[NG];
+#pragma unroll
+            for (int q = 0; q < NG; q++) g[q] = 0.0f;
+            bool contrib = false, branch3d = false;
+
+            if (pos <= last_contributor) {
+                float3 k = pxf * Tw - Tu;
+                float3 l = pyf * Tw - Tv;
+                float3 p = cross(k, l);
+                if (p.z != 0.0f) {
+                    float sx = p.x / p.z, sy = p.y / p.z;
+                    float rho3d = sx * sx + sy * sy;
+                    float dx = r2.y - pxf, dy = r2.z - pyf;
+                    float rho2d = FILTER_INV_SQUARE * (dx * dx + dy * dy);
+                    float rho = fminf(rho3d, rho2d);
+                    float c_d = (rho3d <= rho2d) ? (sx * Tw.x + sy * Tw.y) + Tw.z : Tw.z;
+                    float power = -0.5f * rho;
+                    if (c_d >= NEAR_N && power <= 0.0f) {
+                        const float opa = r2.w;
+                        const float G = expf(power);
+                        const float alpha = fminf(ALPHA_MAX, opa * G);
+                        if (alpha >= ALPHA_MIN) {
+                            contrib = true;
+                            const float4 r3 = s_r3[j];
+                            T = T / (1.0f - alpha);
+                            const float w = alpha * T;
+                            float dL_dalpha = 0.0f;
+#pragma unroll
+                            for (int ch = 0; ch < C; ch++) {
+                                const float c = s_feat[ch * BB + j];
+                                accum_rec[ch] = last_alpha * last_color[ch] + (1.0f - last_alpha) * accum_rec[ch];
+                                last_color[ch] = c;
+                                dL_dalpha += (c - accum_rec[ch]) * dL_dpixel[ch];
+                                g[ch] = w * dL_dpixel[ch];
+                            }
+                            float dL_dz = 0.0f, dL_dweight = 0.0f;
+                            const float m_d = FAR_N / (FAR_N - NEAR_N) * (1.0f - NEAR_N / c_d);
+                            const float dmd_dd = (FAR_N * NEAR_N) / ((FAR_N - NEAR_N) * c_d * c_d);
+                            if (pos == median_contributor) dL_dz += dL_dmedian_depth;
+                            dL_dweight += (final_D2 + m_d * m_d * final_A - 2.0f * m_d * final_D) * dL_dreg;
+                            dL_dalpha += dL_dweight - last_dL_dT;
+                            last_dL_dT = dL_dweight * alpha + (1.0f - alpha) * last_dL_dT;
+                            const float dL_dmd = 2.0f * (T * alpha) * (m_d * final_A - final_D) * dL_dreg;
+                            dL_dz += dL_dmd * dmd_dd;
+
+                            accum_depth_rec = last_alpha * last_depth + (1.0f - last_alpha) * accum_depth_rec;
+                            last_depth = c_d;
+                            dL_dalpha += (c_d - accum_depth_rec) * dL_ddepth;
+                            accum_alpha_rec = last_alpha * 1.0f + (1.0f - last_alpha) * accum_alpha_rec;
+                            dL_dalpha += (1.0f - accum_alpha_rec) * dL_daccum;
+
+                            an0 = last_alpha * ln0 + (1.0f - last_alpha) * an0; ln0 = r3.x;
+                            dL_dalpha += (r3.x - an0) * dL_dn0; g[C + 0] = w * dL_dn0;
+                            an1 = last_alpha * ln1 + (1.0f - last_alpha) * an1; ln1 = r3.y;
+                            dL_dalpha += (r3.y - an1) * dL_dn1; g[C + 1] = w * dL_dn1;
+                            an2 = last_alpha * ln2 + (1.0f - last_alpha) * an2; ln2 = r3.z;
+                            dL_dalpha += (r3.z - an2) * dL_dn2; g[C + 2] = w * dL_dn2;
+
+                            dL_dalpha *= T;
+                            last_alpha = alpha;
+                            dL_dalpha += (-T_final / (1.0f - alpha)) * bg_dot_dpixel;
+
+                            const float dL_dG = opa * dL_dalpha;   // alpha cap is straight-through (backward.cu:391)
+                            dL_dz += w * dL_ddepth;
+                            g[C + 3] = G * dL_dalpha;
+                            if (rho3d <= rho2d) {
+                                branch3d = true;
+                                const float dLdsx = dL_dG * -G * sx + dL_dz * Tw.x;
+                                const float dLdsy = dL_dG * -G * sy + dL_dz * Tw.y;
+                                const float dsx_pz = dLdsx / p.z, dsy_pz = dLdsy / p.z;
+                                const float3 dL_dp = f3(dsx_pz, dsy_pz, -(dsx_pz * sx + dsy_pz * sy));
+                                const float3 dL_dk = cross(l, dL_dp);
+                                const float3 dL_dl = cross(dL_dp, k);
+                                g[C + 4] = -dL_dk.x; g[C + 5] = -dL_dk.y; g[C + 6] = -dL_dk.z;
+                                g[C + 7] = -dL_dl.x; g[C + 8] = -dL_dl.y; g[C + 9] = -dL_dl.z;
+                                g[C + 10] = pxf * dL_dk.x + pyf * dL_dl.x + dL_dz * sx;
+                                g[C + 11] = pxf * dL_dk.y + pyf * dL_dl.y + dL_dz * sy;
+                                g[C + 12] = pxf * dL_dk.z + pyf * dL_dl.z + dL_dz * 1.0f;
+                            } else {
+                                const float dG_ddelx = -G * FILTER_INV_SQUARE * dx;
+                                const float dG_ddely = -G * FILTER_INV_SQUARE * dy;
+                                g[C + 13] = dL_dG * dG_ddelx;
+                                g[C + 14] = dL_dG * dG_ddely;
+                                g[C + 12] = dL_dz;
+                            }
+                        }
+                    }
+                }
+            }
+            const unsigned any_c = __ballot_sync(0xffffffffu, contrib);
+            if (any_c == 0) continue;
+            const bool any3d = __any_sync(0xffffffffu, branch3d);
+            const bool any2d = __any_sync(0xffffffffu, contrib && !branch3d);
+            float* sg = s_g + j * NG;
+#pragma unroll
+            for (int q = 0; q < C + 4; q++) {
+                float v = warp_sum(g[q]);
+                if (lane == 0) atomicAdd(&sg[q], v);
+            }
+            if (any3d) {
+#pragma unroll
+                for (int q = C + 4; q < C + 12; q++) {
+                    float v = warp_sum(g[q]);
+                    if (lane == 0) atomicAdd(&sg[q], v);
+                }
+            }
+            {
+                float v = warp_sum(g[C + 12]);
+                if (lane == 0) atomicAdd(&sg[C + 12], v);
+            }
+            if (any2d) {
+#pragma unroll
+                for (int q = C + 13; q < C + 15; q++) {
+                    float v = warp_sum(g[q]);
+                    if (lane == 0) atomicAdd(&sg[q], v);
+                }
+            }
+        }
+        __syncthreads();
+        // flush this batch: thread t owns surfel slot t
+        if (tid < nb) {
+            const int id = s_id[tid];
+            float* sg = s_g + tid * NG;
+#pragma unroll
+            for (int q = 0; q < NG; q++) {
+                float v = sg[q];
+                if (v != 0.0f) {
+                    sg[q] = 0.0f;
+                    if (q < C) atomicAdd(&dL_dcolors[(size_t)id * C + q], v);
+                    else if (q < C + 3) atomicAdd(&dL_dnormal3D[(size_t)id * 3 + (q - C)], v);
+                    else if (q == C + 3) atomicAdd(&dL_dopacity[id], v);
+                    else if (q < C + 13) atomicAdd(&dL_dtransMat[(size_t)id * 9 + (q - C - 4)], v);
+                    else atomicAdd(&dL_dmean2D[(size_t)id * 3 + (q - C - 13)], v);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(256) preprocess_bwd_kernel(
+    int P, int D, int M, const float* __restrict__ means3D, const int* __restrict__ radii,
+    const float* __restrict__ shs, const uint8_t* __restrict__ clamped, const float2* __restrict__ scales,
+    const float4* __restrict__ rotations, const float* __restrict__ transMat_precomp, const float4* __restrict__ rec,
+    const float* __restrict__ viewmatrix, const float* __restrict__ pm, float focal_x, float focal_y, float tan_fovx,
+    float tan_fovy, const float* __restrict__ campos, float* __restrict__ dL_dtransMats,
+    const float* __restrict__ dL_dnormal3Ds, const float* __restrict__ dL_dcolors, float* __restrict__ dL_dshs,
+    float* __restrict__ dL_dmean2Ds, float* __restrict__ dL_dmean3Ds, float* __restrict__ dL_dscales,
+    float* __restrict__ dL_drots) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P || !(radii[idx] > 0)) return;
+    // the reference recomputes the image size from the focal length (backward.cu:607-608)
+    const int W = int(focal_x * tan_fovx * 2);
+    const int H = int(focal_y * tan_fovy * 2);
+
+    float* dT = dL_dtransMats + 9 * (size_t)idx;
+    const float dT_render2 = dT[2], dT_render5 = dT[5];   // densification signal uses the render-only part
+    float3 gTu = f3(dT[0], dT[1], dT[2]), gTv = f3(dT[3], dT[4], dT[5]), gTw = f3(dT[6], dT[7], dT[8]);
+
+    float3 Tu, Tv, Tw, normal = f3(0, 0, 0);
+    float3 p_orig = ld3(means3D, idx);
+    float2 scale = make_float2(0, 0);
+    float4 rot = make_float4(1, 0, 0, 0);
+    Rot3 R;
+    float Q[3][4];   // Q = N * PV (3x4)
+    const bool precomp = (scales == nullptr);
+    if (precomp) {
+        const float* t = transMat_precomp + 9 * (size_t)idx;
+        Tu = f3(t[0], t[1], t[2]); Tv = f3(t[3], t[4], t[5]); Tw = f3(t[6], t[7], t[8]);
+    } else {
+        scale = scales[idx];
+        rot = rotations[idx];
+        R = quat_to_rot(rot);
+        float3 L0 = R.c0 * scale.x, L1 = R.c1 * scale.y;   // scale_modifier ignored here (backward.cu:481)
+        float hw = float(W) / 2.0f, cw = float(W - 1) / 2.0f, hh = float(H) / 2.0f, chh = float(H - 1) / 2.0f;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            float pv0 = pm[4 * r + 0], pv1 = pm[4 * r + 1], pv3 = pm[4 * r + 3];   // PV[i][r] = pm[4*r + i]
+            Q[0][r] = pv0 * hw + pv3 * cw;
+            Q[1][r] = pv1 * hh + pv3 * chh;
+            Q[2][r] = pv3;
+        }
+        // T rows = Q * S
+        float4 s0 = make_float4(L0.x, L0.y, L0.z, 0.0f), s1 = make_float4(L1.x, L1.y, L1.z, 0.0f),
+               s2 = make_float4(p_orig.x, p_orig.y, p_orig.z, 1.0f);
+        auto row = [&](int i) {
+            return f3(Q[i][0] * s0.x + Q[i][1] * s0.y + Q[i][2] * s0.z + Q[i][3] * s0.w,
+                      Q[i][0] * s1.x + Q[i][1] * s1.y + Q[i][2] * s1.z + Q[i][3] * s1.w,
+                      Q[i][0] * s2.x + Q[i][1] * s2.y + Q[i][2] * s2.z + Q[i][3] * s2.w);
+        };
+        Tu = row(0); Tv = row(1); Tw = row(2);
+        normal = xform_vec_4x3(R.c2, viewmatrix);
+    }
+
+    const float m2x = dL_dmean2Ds[3 * (size_t)idx + 0], m2y = dL_dmean2Ds[3 * (size_t)idx + 1];
+    if (m2x != 0.0f || m2y != 0.0f) {   // backward.cu:515-543
+        float3 t_vec = f3(9.0f, 9.0f, -1.0f);
+        float d = dot(t_vec, Tw * Tw);
+        float3 f_vec = t_vec * (1.0f / d);
+        float3 dT0 = m2x * f_vec * Tw;
+        float3 dT1 = m2y * f_vec * Tw;
+        float3 dT3 = m2x * f_vec * Tu + m2y * f_vec * Tv;
+        float3 dL_df = m2x * Tu * Tw + m2y * Tv * Tw;
+        float dL_dd = dot(dL_df, f_vec) * (-1.0f / d);
+        float3 dd_dT3 = t_vec * Tw * 2.0f;
+        dT3 += dL_dd * dd_dT3;
+        gTu += dT0; gTv += dT1; gTw += dT3;
+        if (precomp) {
+            dT[0] = gTu.x; dT[1] = gTu.y; dT[2] = gTu.z; dT[3] = gTv.x; dT[4] = gTv.y; dT[5] = gTv.z;
+            dT[6] = gTw.x; dT[7] = gTw.y; dT[8] = gTw.z;
+        }
+    }
+
+    if (!precomp) {
+        // dL/dS = Q^T * [gTu; gTv; gTw]  (4x3); columns: d/dL0, d/dL1, d/d(p,1)
+        float dS[4][3];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            dS[r][0] = Q[0][r] * gTu.x + Q[1][r] * gTv.x + Q[2][r] * gTw.x;
+            dS[r][1] = Q[0][r] * gTu.y + Q[1][r] * gTv.y + Q[2][r] * gTw.y;
+            dS[r][2] = Q[0][r] * gTu.z + Q[1][r] * gTv.z + Q[2][r] * gTw.z;
+        }
+        float3 dL_dtn = xform_vec_4x3_T(ld3(dL_dnormal3Ds, idx), viewmatrix);
+        float3 p_view = xform_point_4x3(p_orig, viewmatrix);
+        float cosv = -sum3(p_view * normal);
+        float mult = cosv > 0.0f ? 1.0f : -1.0f;
+        dL_dtn = mult * dL_dtn;
+        float3 dRS0 = f3(dS[0][0], dS[1][0], dS[2][0]), dRS1 = f3(dS[0][1], dS[1][1], dS[2][1]);
+        Rot3 dR;
+        dR.c0 = dRS0 * scale.x; dR.c1 = dRS1 * scale.y; dR.c2 = dL_dtn;
+        float4 dq = quat_to_rot_vjp(rot, dR);
+        dL_drots[4 * (size_t)idx + 0] = dq.x; dL_drots[4 * (size_t)idx + 1] = dq.y;
+        dL_drots[4 * (size_t)idx + 2] = dq.z; dL_drots[4 * (size_t)idx + 3] = dq.w;
+        dL_dscales[2 * (size_t)idx + 0] = dot(dRS0, R.c0);
+        dL_dscales[2 * (size_t)idx + 1] = dot(dRS1, R.c1);
+        dL_dmean3Ds[3 * (size_t)idx + 0] = dS[0][2];
+        dL_dmean3Ds[3 * (size_t)idx + 1] = dS[1][2];
+        dL_dmean3Ds[3 * (size_t)idx + 2] = dS[2][2];
+    }
+
+    if (shs != nullptr) {   // SH backward (backward.cu:20-139); C == 3
+        float3 cam = f3(campos[0], campos[1], campos[2]);
+        float3 dir_orig = p_orig - cam;
+        float3 dir = dir_orig / length3(dir_orig);
+        const float* sh = shs + (size_t)idx * M * 3;
+        float3 dRGB = ld3(dL_dcolors, idx);
+        dRGB.x *= clamped[3 * idx + 0] ? 0.0f : 1.0f;
+        dRGB.y *= clamped[3 * idx + 1] ? 0.0f : 1.0f;
+        dRGB.z *= clamped[3 * idx + 2] ? 0.0f : 1.0f;
+        float b[16];
+        sh_basis(D, dir, b);
+        float* dsh = dL_dshs + (size_t)idx * M * 3;
+        int nb = (D + 1) * (D + 1);
+        for (int k = 0; k < nb; k++) { dsh[3 * k] = b[k] * dRGB.x; dsh[3 * k + 1] = b[k] * dRGB.y; dsh[3 * k + 2] = b[k] * dRGB.z; }
+        float3 gx, gy, gz;
+        sh_dir_grad(D, dir, sh, gx, gy, gz);
+        float3 dL_ddir = f3(dot(gx, dRGB), dot(gy, dRGB), dot(gz, dRGB));
+        float3 dm = dnormvdv(dir_orig, dL_ddir);
+        dL_dmean3Ds[3 * (size_t)idx + 0] += dm.x;
+        dL_dmean3Ds[3 * (size_t)idx + 1] += dm.y;
+        dL_dmean3Ds[3 * (size_t)idx + 2] += dm.z;
+    }
+
+    // densification signal (backward.cu:626-629): depth = forward transMat[8] = Tw.z of the stored record
+    float depth = precomp ? transMat_precomp[9 * (size_t)idx + 8] : rec[4 * (size_t)idx + 2].x;
+    dL_dmean2Ds[3 * (size_t)idx + 0] = dT_render2 * depth * 0.5f * float(W);
+    dL_dmean2Ds[3 * (size_t)idx + 1] = dT_render5 * depth * 0.5f * float(H);
+}
+
+template <int C>
+static int raster_backward_impl(const envgs_raster_args& a, const int* radii_in, int R, char* geom_buffer,
+                                char* binning_buffer, char* img_buffer, const envgs_raster_grads& gr,
+                                cudaStream_t stream) {
+    const int P = a.P, W = a.width, H = a.height;
+    const int gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y;
+    const bool debug = a.debug != 0;
+    GeomState g;
+    GeomState::carve(geom_buffer, P, &g, scan_temp_bytes(P));
+    ImageState im;
+    ImageState::carve(img_buffer, W, H, &im);
+    BinningState b;
+    BinningState::carve(binning_buffer, R, &b, sort_temp_bytes(R));
+    const int* radii = radii_in ? radii_in : g.internal_radii;
+    const float focal_y = H / (2.0f * a.tan_fovy), focal_x = W / (2.0f * a.tan_fovx);
+    const float* feat = a.colors_precomp ? a.colors_precomp : g.rgb;
+
+    if (R > 0) {
+        render_bwd_kernel<C><<<gx * gy, 256, 0, stream>>>(im.ranges, b.point_list, W, H, gx, a.background, g.rec,
+                                                          g.pixbox, feat, im.final_T, im.n_contrib, gr.dL_dout_color,
+                                                          gr.dL_dout_others, gr.dL_dtransMat, gr.dL_dmeans2D,
+                                                          gr.dL_dnormal, gr.dL_dopacity, gr.dL_dcolors);
+        ENVGS_LAUNCH_CHECK("render_bwd", debug, stream);
+    }
+    preprocess_bwd_kernel<C><<<(P + 255) / 256, 256, 0, stream>>>(
+        P, a.sh_degree, a.sh_coeffs, a.means3D, radii, a.shs, g.clamped, (const float2*)a.scales,
+        (const float4*)a.rotations, a.transMat_precomp, g.rec, a.viewmatrix, a.projmatrix, focal_x, focal_y, a.tan_fovx,
+        a.tan_fovy, a.campos, gr.dL_dtransMat, gr.dL_dnormal, gr.dL_dcolors, gr.dL_dsh, gr.dL_dmeans2D, gr.dL_dmeans3D,
+        gr.dL_dscales, gr.dL_drotations);
+    ENVGS_LAUNCH_CHECK("preprocess_bwd", debug, stream);
+    return ENVGS_OK;
+}
+
+int raster_backward_dispatch(const envgs_raster_args& a, const int* radii, int R, void* geom, void* binning, void* img,
+                             const envgs_raster_grads& gr, cudaStream_t stream) {
+    switch (a.C) {
+        case 3: return raster_backward_impl<3>(a, radii, R, (char*)geom, (char*)binning, (char*)img, gr, stream);
+        case 5: return raster_backward_impl<5>(a, radii, R, (char*)geom, (char*)binning, (char*)img, gr, stream);
+        case 7: return raster_backward_impl<7>(a, radii, R, (char*)geom, (char*)binning, (char*)img, gr, stream);
+        default: set_error("unsupported channel count C=%d (3, 5 or 7)", a.C); return ENVGS_ERR_INVALID;
+    }
+}
+
+}  // namespace envgs

@@ -1,0 +1,201 @@
+/*
+ * envgs_b200.h — C ABI of libenvgs_b200.so: the B200-native (sm_100a) replacement for the two native
+ * submodules of zju3dv/EnvGS' per-view rendering hot path.
+ *
+ *   surfel rasterizer  (replaces diff-surfel-rasterization-wet[-ch05|-ch07], pybind11 module `_C`)
+ *   surfel tracer      (replaces diff-surfel-tracing: OptiX GAS + raygen/anyhit programs)
+ *
+ * Every pointer is caller-owned DEVICE memory (contiguous fp32 / int32), every `stream` is a cudaStream_t
+ * passed as void*.  No torch types cross this boundary.  Functions return 0 (or a non-negative count) on
+ * success and a negative code on failure; envgs_last_error() then holds a message.  Nothing here
+ * synchronises the stream except the 4-byte read-back of the instance count in envgs_raster_forward
+ * (the reference does the same: rasterizer_impl.cu:283).
+ *
+ * Reference interfaces replaced (paths relative to /root/reference/submodules):
+ *   envgs_raster_forward   <- RasterizeGaussiansCUDA            diff-surfel-rasterizations/diff-surfel-rasterization-wet-ch05/rasterize_points.cu:39-136
+ *                             CudaRasterizer::Rasterizer::forward  .../cuda_rasterizer/rasterizer_impl.cu:198-344
+ *   envgs_raster_backward  <- RasterizeGaussiansBackwardCUDA    .../rasterize_points.cu:138-235, rasterizer_impl.cu:348-450
+ *   envgs_mark_visible     <- markVisible                       .../rasterize_points.cu:237-256
+ *   envgs_tracer_create/destroy <- OptiXStateWrapper            diff-surfel-tracing/optix_tracer/optix_wrapper.cpp:177-233
+ *   envgs_tracer_build     <- BuildAccelerationStructure        diff-surfel-tracing/trace_surfels.cpp:47-170
+ *   envgs_trace_forward    <- TraceSurfelsCUDA                  diff-surfel-tracing/trace_surfels.cpp:173-315
+ *   envgs_trace_backward   <- TraceSurfelsBackwardCUDA          diff-surfel-tracing/trace_surfels.cpp:318-471
+ */
+#ifndef ENVGS_B200_H_
+#define ENVGS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ENVGS_OK 0
+#define ENVGS_ERR_INVALID -1   /* bad argument (shape, null pointer, unsupported channel count ...) */
+#define ENVGS_ERR_CUDA -2      /* a CUDA runtime call failed */
+#define ENVGS_ERR_ALLOC -3     /* an allocator callback returned NULL */
+#define ENVGS_ERR_STATE -4     /* e.g. trace before build */
+
+/* Scratch allocator: must return >= nbytes of device memory, 256-byte aligned, that stays valid until the
+ * matching backward call finished (the reference uses resizable torch byte tensors the same way:
+ * rasterize_points.cu:31-37). */
+typedef void* (*envgs_alloc_fn)(void* user, size_t nbytes);
+
+const char* envgs_last_error(void);
+int envgs_version(void);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* Rasterizer                                                                                         */
+/* ------------------------------------------------------------------------------------------------ */
+
+typedef struct envgs_raster_args {
+    int32_t P;              /* number of surfels */
+    int32_t C;              /* feature channels: 3 (wet), 5 (wet_ch05), 7 (wet_ch07) */
+    int32_t sh_degree;      /* active SH degree D (0..3); used only when shs != NULL */
+    int32_t sh_coeffs;      /* M = coefficients stored per surfel in `shs` */
+    int32_t width, height;
+    float tan_fovx, tan_fovy;
+    float scale_modifier;
+    int32_t prefiltered, debug;
+    const float* background;       /* (C,)           */
+    const float* means3D;          /* (P,3)          */
+    const float* shs;              /* (P,M,3) or NULL (only legal when C == 3) */
+    const float* colors_precomp;   /* (P,C)  or NULL */
+    const float* opacities;        /* (P,1)          */
+    const float* scales;           /* (P,2)  or NULL when transMat_precomp given */
+    const float* rotations;        /* (P,4) wxyz or NULL */
+    const float* transMat_precomp; /* (P,9)  or NULL */
+    const float* viewmatrix;       /* (4,4) W2C^T, contiguous        */
+    const float* projmatrix;       /* (4,4) (Proj*W2C)^T, contiguous */
+    const float* campos;           /* (3,)           */
+} envgs_raster_args;
+
+typedef struct envgs_raster_out {
+    float* out_color;   /* (C,H,W)  written                         */
+    float* out_others;  /* (7,H,W)  written: [depth*a, a, nx,ny,nz, median depth, distortion] */
+    float* out_weight;  /* (P,1)    accumulated (must be zeroed by caller) */
+    int32_t* radii;     /* (P,)     written                         */
+} envgs_raster_out;
+
+/* Returns num_rendered (instances in the binned list, >= 0) or a negative error.  The three scratch
+ * buffers are opaque; hand the same pointers to envgs_raster_backward. */
+int envgs_raster_forward(const envgs_raster_args* args, const envgs_raster_out* out,
+                         envgs_alloc_fn geom_alloc, envgs_alloc_fn binning_alloc, envgs_alloc_fn img_alloc,
+                         void* alloc_user, void* stream);
+
+typedef struct envgs_raster_grads {
+    const float* dL_dout_color;   /* (C,H,W) */
+    const float* dL_dout_others;  /* (7,H,W) */
+    /* outputs, all must be zero-filled by the caller */
+    float* dL_dmeans2D;    /* (P,3) densification signal (backward.cu:626-629) */
+    float* dL_dcolors;     /* (P,C) */
+    float* dL_dopacity;    /* (P,1) */
+    float* dL_dmeans3D;    /* (P,3) */
+    float* dL_dtransMat;   /* (P,9) */
+    float* dL_dsh;         /* (P,M,3) or NULL */
+    float* dL_dscales;     /* (P,2) */
+    float* dL_drotations;  /* (P,4) */
+    float* dL_dnormal;     /* (P,3) scratch */
+} envgs_raster_grads;
+
+int envgs_raster_backward(const envgs_raster_args* args, const int32_t* radii, int32_t num_rendered,
+                          void* geom_buffer, void* binning_buffer, void* img_buffer,
+                          const envgs_raster_grads* grads, void* stream);
+
+/* present[i] = view-space z of means3D[i] > 0.2 (auxiliary.h:185-210) */
+int envgs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                       uint8_t* present, void* stream);
+
+/* sizes of the fixed-size scratch regions, for callers that pre-allocate */
+size_t envgs_raster_geom_bytes(int32_t P);
+size_t envgs_raster_img_bytes(int32_t width, int32_t height);
+size_t envgs_raster_binning_bytes(int32_t num_rendered);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* Tracer                                                                                             */
+/* ------------------------------------------------------------------------------------------------ */
+
+typedef struct envgs_tracer envgs_tracer;
+
+envgs_tracer* envgs_tracer_create(void);
+void envgs_tracer_destroy(envgs_tracer* h);
+
+/* Build (rebuild != 0) or refit (rebuild == 0, same P as the last build) the LBVH over the P surfel quads
+ * given as 4P vertices in the reference's order [(-,+),(-,-),(+,+),(+,-)] (optix_utils.py:39-69).  BVH
+ * storage comes from `alloc` (called at most once per build when capacity must grow; the handle keeps the
+ * pointer).  Pass alloc == NULL to let the library cudaMallocAsync/cudaFreeAsync on `stream`. */
+int envgs_tracer_build(envgs_tracer* h, const float* vertices, int32_t num_vertices, int32_t rebuild,
+                       envgs_alloc_fn alloc, void* alloc_user, void* stream);
+size_t envgs_tracer_bvh_bytes(int32_t P);
+
+typedef struct envgs_trace_args {
+    int32_t P;          /* surfels (must equal the built P) */
+    int32_t H, W;       /* rays are (H,W,3) */
+    int32_t sh_degree, sh_coeffs;
+    int32_t training;   /* accumulate per-surfel weights */
+    int32_t start_from_first;
+    int32_t max_trace_depth;     /* 0 or 1 (MAX_TRACE_DEPTH, config.h:38) */
+    float specular_threshold;
+    float scale_modifier;
+    const float* ray_o;          /* (H,W,3) */
+    const float* ray_d;          /* (H,W,3) */
+    const float* background;     /* (3,) */
+    const float* means3D;        /* (P,3) */
+    const float* shs;            /* (P,M,3) or NULL */
+    const float* colors_precomp; /* (P,3) or NULL */
+    const float* others_precomp; /* (P,2) or NULL */
+    const float* opacities;      /* (P,1) */
+    const float* scales;         /* (P,2) */
+    const float* rotations;      /* (P,4) */
+    const float* viewmatrix;     /* (4,4) */
+    const float* projmatrix;     /* (4,4) */
+    const float* campos;         /* (3,) */
+} envgs_trace_args;
+
+typedef struct envgs_trace_out {   /* all written for every ray; a_weights accumulated (zeroed by caller) */
+    float* out_rgb;   /* (H,W,3)  */
+    float* out_dpt;   /* (H,W,1)  */
+    float* out_acc;   /* (H,W,1)  */
+    float* out_norm;  /* (H,W,3)  */
+    float* out_dist;  /* (H,W,3)  [distortion, M1, M2] */
+    float* out_aux;   /* (H,W,2)  */
+    float* mid_val;   /* (H,W,32) zero-filled by caller */
+    float* a_weights; /* (P,1) or NULL when !training */
+} envgs_trace_out;
+
+int envgs_trace_forward(envgs_tracer* h, const envgs_trace_args* args, const envgs_trace_out* out, void* stream);
+
+typedef struct envgs_trace_grads {
+    /* saved forward outputs */
+    const float* out_rgb; const float* out_dpt; const float* out_acc; const float* out_norm;
+    const float* out_dist; const float* out_aux; const float* mid_val;
+    /* upstream */
+    const float* dL_drgb;  /* (H,W,3) */
+    const float* dL_ddpt;  /* (H,W,1) */
+    const float* dL_dacc;  /* (H,W,1) */
+    const float* dL_dnorm; /* (H,W,3) */
+    const float* dL_ddist; /* (H,W,1) */
+    const float* dL_daux;  /* (H,W,2) */
+    /* outputs: ray grads written, per-surfel grads accumulated (zeroed by caller) */
+    float* dL_dray_o;      /* (H,W,3) */
+    float* dL_dray_d;      /* (H,W,3) */
+    float* dL_dmeans3D;    /* (P,3) */
+    float* dL_dshs;        /* (P,M,3) or NULL */
+    float* dL_dcolors;     /* (P,3) */
+    float* dL_dothers;     /* (P,2) or NULL */
+    float* dL_dopacities;  /* (P,1) */
+    float* dL_dscales;     /* (P,2) */
+    float* dL_drotations;  /* (P,4) */
+} envgs_trace_grads;
+
+int envgs_trace_backward(envgs_tracer* h, const envgs_trace_args* args, const envgs_trace_grads* grads,
+                         void* stream);
+
+/* Kernel-launch counter (every kernel this library launches increments it); bench.py reports it. */
+uint64_t envgs_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ENVGS_B200_H_ */
