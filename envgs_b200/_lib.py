@@ -71,7 +71,7 @@ EXPORTS = [
     "envgs_last_error", "envgs_version", "envgs_raster_forward", "envgs_raster_backward", "envgs_mark_visible",
     "envgs_raster_geom_bytes", "envgs_raster_img_bytes", "envgs_raster_binning_bytes", "envgs_tracer_create",
     "envgs_tracer_destroy", "envgs_tracer_build", "envgs_tracer_bvh_bytes", "envgs_trace_forward",
-    "envgs_trace_backward", "envgs_launch_count",
+    "envgs_trace_backward", "envgs_launch_count", "envgs_profile_enable", "envgs_profile_report",
 ]
 
 _lib = None
@@ -112,6 +112,10 @@ def lib() -> C.CDLL:
     L.envgs_trace_forward.argtypes = [C.c_void_p, C.POINTER(TraceArgs), C.POINTER(TraceOut), C.c_void_p]
     L.envgs_trace_backward.restype = C.c_int
     L.envgs_trace_backward.argtypes = [C.c_void_p, C.POINTER(TraceArgs), C.POINTER(TraceGrads), C.c_void_p]
+    L.envgs_profile_enable.restype = None
+    L.envgs_profile_enable.argtypes = [C.c_int]
+    L.envgs_profile_report.restype = C.c_size_t
+    L.envgs_profile_report.argtypes = [C.c_char_p, C.c_size_t]
     _lib = L
     return L
 
@@ -132,3 +136,18 @@ def ptr(t) -> int | None:
 
 def launch_count() -> int:
     return int(lib().envgs_launch_count())
+
+
+def profile_enable(on: bool) -> None:
+    lib().envgs_profile_enable(int(bool(on)))
+
+
+def profile_report() -> dict:
+    """{kernel name: (launches, total device ms)} since the last report (CUDA events on the launching stream)."""
+    buf = C.create_string_buffer(1 << 16)
+    lib().envgs_profile_report(buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.split()
+        out[name] = (int(cnt), float(ms))
+    return out

@@ -2,6 +2,9 @@
 #include <stdarg.h>
 #include <atomic>
 #include <mutex>
+#include <map>
+#include <string>
+#include <vector>
 #include <string.h>
 #include "lbvh.cuh"
 #include "raster_state.cuh"
@@ -18,6 +21,27 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+struct ProfRecord { const char* name; cudaEvent_t start, stop; };
+static bool g_profile = false;
+static std::mutex g_prof_mutex;
+static std::vector<ProfRecord> g_prof_records;
+
+KernelTimer::KernelTimer(const char* name, cudaStream_t s) : slot(-1), stream(s) {
+    if (!g_profile) return;
+    ProfRecord r;
+    r.name = name;
+    if (cudaEventCreate(&r.start) != cudaSuccess || cudaEventCreate(&r.stop) != cudaSuccess) return;
+    cudaEventRecord(r.start, s);
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    g_prof_records.push_back(r);
+    slot = (int)g_prof_records.size() - 1;
+}
+KernelTimer::~KernelTimer() {
+    if (slot < 0) return;
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    cudaEventRecord(g_prof_records[slot].stop, stream);
+}
 
 int raster_forward_dispatch(const envgs_raster_args& a, const envgs_raster_out& o, envgs_alloc_fn ga, envgs_alloc_fn ba,
                             envgs_alloc_fn ia, void* user, cudaStream_t stream);
@@ -41,6 +65,36 @@ extern "C" {
 const char* envgs_last_error(void) { return g_error; }
 int envgs_version(void) { return 100; }
 uint64_t envgs_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+void envgs_profile_enable(int on) { g_profile = on != 0; }
+
+size_t envgs_profile_report(char* buf, size_t n) {
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    std::map<std::string, std::pair<int, double>> acc;
+    for (auto& r : g_prof_records) {
+        float ms = 0.0f;
+        if (cudaEventSynchronize(r.stop) == cudaSuccess && cudaEventElapsedTime(&ms, r.start, r.stop) == cudaSuccess) {
+            auto& e = acc[r.name];
+            e.first += 1;
+            e.second += ms;
+        }
+        cudaEventDestroy(r.start);
+        cudaEventDestroy(r.stop);
+    }
+    g_prof_records.clear();
+    std::string out;
+    char line[256];
+    for (auto& kv : acc) {
+        snprintf(line, sizeof(line), "%s %d %.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+        out += line;
+    }
+    if (buf && n > 0) {
+        size_t m = out.size() < n - 1 ? out.size() : n - 1;
+        memcpy(buf, out.data(), m);
+        buf[m] = 0;
+    }
+    return out.size() + 1;
+}
 
 static int check_raster_args(const envgs_raster_args* a) {
     if (!a) { set_error("args is NULL"); return ENVGS_ERR_INVALID; }

@@ -32,6 +32,15 @@ __device__ __constant__ const float SH_C3[7] = {-0.5900435899266435f, 2.89061144
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 
+// Optional per-kernel timing with CUDA events on the launching stream (envgs_profile_enable); a no-op otherwise.
+struct KernelTimer {
+    KernelTimer(const char* name, cudaStream_t stream);
+    ~KernelTimer();
+    int slot;
+    cudaStream_t stream;
+};
+#define ENVGS_TIMED(name, stream) ::envgs::KernelTimer _envgs_kt_##__LINE__(name, stream)
+
 #define ENVGS_CUDA_TRY(expr)                                                                      \
     do {                                                                                          \
         cudaError_t _e = (expr);                                                                  \

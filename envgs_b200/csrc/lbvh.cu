@@ -235,6 +235,7 @@ __global__ void single_prim_kernel(const float4* __restrict__ leaf_lo, const flo
 
 int lbvh_build(Lbvh& t, const float* vertices, int P, bool rebuild, cudaStream_t stream) {
     if (P <= 0) { t.P = 0; return ENVGS_OK; }
+    ENVGS_TIMED("bvh_build", stream);
     if (!rebuild && t.P != P) rebuild = true;   // topology can only be reused for the same surfel count
     uint32_t* bounds = reinterpret_cast<uint32_t*>(t.bounds);
     int blocks = (P + 255) / 256;

@@ -397,12 +397,14 @@ static int raster_backward_impl(const envgs_raster_args& a, const int* radii_in,
     const float* feat = a.colors_precomp ? a.colors_precomp : g.rgb;
 
     if (R > 0) {
+        ENVGS_TIMED("render_bwd", stream);
         render_bwd_kernel<C><<<gx * gy, 256, 0, stream>>>(im.ranges, b.point_list, W, H, gx, a.background, g.rec,
                                                           g.pixbox, feat, im.final_T, im.n_contrib, gr.dL_dout_color,
                                                           gr.dL_dout_others, gr.dL_dtransMat, gr.dL_dmeans2D,
                                                           gr.dL_dnormal, gr.dL_dopacity, gr.dL_dcolors);
         ENVGS_LAUNCH_CHECK("render_bwd", debug, stream);
     }
+    ENVGS_TIMED("preprocess_bwd", stream);
     preprocess_bwd_kernel<C><<<(P + 255) / 256, 256, 0, stream>>>(
         P, a.sh_degree, a.sh_coeffs, a.means3D, radii, a.shs, g.clamped, (const float2*)a.scales,
         (const float4*)a.rotations, a.transMat_precomp, g.rec, a.viewmatrix, a.projmatrix, focal_x, focal_y, a.tan_fovx,

@@ -438,14 +438,19 @@ static int raster_forward_impl(const envgs_raster_args& a, const envgs_raster_ou
 
     int* radii = o.radii ? o.radii : g.internal_radii;
 
-    preprocess_kernel<C><<<(P + 255) / 256, 256, 0, stream>>>(
-        P, a.sh_degree, a.sh_coeffs, a.means3D, (const float2*)a.scales, a.scale_modifier, (const float4*)a.rotations,
-        a.opacities, a.shs, a.transMat_precomp, a.colors_precomp, a.viewmatrix, a.projmatrix, a.campos, W, H, gx, gy,
-        radii, g);
-    ENVGS_LAUNCH_CHECK("preprocess", debug, stream);
-
-    ENVGS_CUDA_TRY(cub::DeviceScan::InclusiveSum(g.scan_temp, g.scan_temp_bytes, g.tiles_touched, g.point_offsets, P, stream));
-    count_launch(2);
+    {
+        ENVGS_TIMED("preprocess_fwd", stream);
+        preprocess_kernel<C><<<(P + 255) / 256, 256, 0, stream>>>(
+            P, a.sh_degree, a.sh_coeffs, a.means3D, (const float2*)a.scales, a.scale_modifier, (const float4*)a.rotations,
+            a.opacities, a.shs, a.transMat_precomp, a.colors_precomp, a.viewmatrix, a.projmatrix, a.campos, W, H, gx, gy,
+            radii, g);
+        ENVGS_LAUNCH_CHECK("preprocess", debug, stream);
+    }
+    {
+        ENVGS_TIMED("scan", stream);
+        ENVGS_CUDA_TRY(cub::DeviceScan::InclusiveSum(g.scan_temp, g.scan_temp_bytes, g.tiles_touched, g.point_offsets, P, stream));
+        count_launch(2);
+    }
 
     int num_rendered = 0;
     ENVGS_CUDA_TRY(cudaMemcpyAsync(&num_rendered, g.point_offsets + P - 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
@@ -460,21 +465,33 @@ static int raster_forward_impl(const envgs_raster_args& a, const envgs_raster_ou
 
     ENVGS_CUDA_TRY(cudaMemsetAsync(im.ranges, 0, (size_t)gx * gy * sizeof(uint2), stream));
     if (num_rendered > 0) {
-        duplicate_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, g, b.keys_unsorted, b.vals_unsorted, gx);
-        ENVGS_LAUNCH_CHECK("duplicate", debug, stream);
+        {
+            ENVGS_TIMED("duplicate", stream);
+            duplicate_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, g, b.keys_unsorted, b.vals_unsorted, gx);
+            ENVGS_LAUNCH_CHECK("duplicate", debug, stream);
+        }
         int bit = (int)higher_msb((uint32_t)(gx * gy));
-        ENVGS_CUDA_TRY(cub::DeviceRadixSort::SortPairs(b.sort_temp, b.sort_temp_bytes, b.keys_unsorted, b.keys,
-                                                       b.vals_unsorted, b.point_list, num_rendered, 0, 32 + bit, stream));
-        count_launch(8);
-        tile_ranges_kernel<<<(num_rendered + 255) / 256, 256, 0, stream>>>(num_rendered, b.keys, im.ranges);
-        ENVGS_LAUNCH_CHECK("tile_ranges", debug, stream);
+        {
+            ENVGS_TIMED("sort", stream);
+            ENVGS_CUDA_TRY(cub::DeviceRadixSort::SortPairs(b.sort_temp, b.sort_temp_bytes, b.keys_unsorted, b.keys,
+                                                           b.vals_unsorted, b.point_list, num_rendered, 0, 32 + bit, stream));
+            count_launch(8);
+        }
+        {
+            ENVGS_TIMED("tile_ranges", stream);
+            tile_ranges_kernel<<<(num_rendered + 255) / 256, 256, 0, stream>>>(num_rendered, b.keys, im.ranges);
+            ENVGS_LAUNCH_CHECK("tile_ranges", debug, stream);
+        }
     }
 
     const float* feat = a.colors_precomp ? a.colors_precomp : g.rgb;
-    render_fwd_kernel<C><<<gx * gy, 256, 0, stream>>>(im.ranges, b.point_list, W, H, gx, g.rec, g.pixbox, feat,
-                                                      a.background, im.final_T, im.n_contrib, o.out_color, o.out_others,
-                                                      o.out_weight);
-    ENVGS_LAUNCH_CHECK("render_fwd", debug, stream);
+    {
+        ENVGS_TIMED("render_fwd", stream);
+        render_fwd_kernel<C><<<gx * gy, 256, 0, stream>>>(im.ranges, b.point_list, W, H, gx, g.rec, g.pixbox, feat,
+                                                          a.background, im.final_T, im.n_contrib, o.out_color, o.out_others,
+                                                          o.out_weight);
+        ENVGS_LAUNCH_CHECK("render_fwd", debug, stream);
+    }
     return num_rendered;
 }
 

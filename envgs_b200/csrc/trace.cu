@@ -597,6 +597,7 @@ static int launch_trace(bool bwd, Lbvh& bvh, unsigned int* counter, const envgs_
     int blocks = sm_count * (bwd ? occ_b : occ_f);
     int need = (p.n_items + (TR_THREADS / 32) - 1) / (TR_THREADS / 32);
     if (blocks > need) blocks = need > 0 ? need : 1;
+    ENVGS_TIMED(bwd ? "trace_bwd" : "trace_fwd", stream);
     if (bwd) trace_kernel<true><<<blocks, TR_THREADS, 0, stream>>>(p);
     else trace_kernel<false><<<blocks, TR_THREADS, 0, stream>>>(p);
     ENVGS_LAUNCH_CHECK(bwd ? "trace_bwd" : "trace_fwd", false, stream);

@@ -195,6 +195,13 @@ int envgs_trace_backward(envgs_tracer* h, const envgs_trace_args* args, const en
 /* Kernel-launch counter (every kernel this library launches increments it); bench.py reports it. */
 uint64_t envgs_launch_count(void);
 
+/* Per-kernel device timing (CUDA events recorded on the launching stream around each kernel / library primitive).
+ * Off by default.  envgs_profile_report synchronises the recorded events, writes one line per kernel name
+ * ("name count total_ms\n") into buf (NUL-terminated, truncated to n) and clears the records; returns the
+ * number of bytes the full report needs. */
+void envgs_profile_enable(int on);
+size_t envgs_profile_report(char* buf, size_t n);
+
 #ifdef __cplusplus
 }
 #endif

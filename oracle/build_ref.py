@@ -1,0 +1,66 @@
+"""ORACLE tooling (checker only): compile the UNMODIFIED reference rasterizer extensions for sm_100a.
+
+Sources are compiled where they lie under /root/reference (never copied into this repository); outputs go to
+oracle/_ref/ (git-ignored, but shipped to the GPU box by gpurun).  The resulting modules are used only by
+`oracle/make_golden.py` (to generate tests/golden/*.pt on a B200) and by the optional live comparison in
+tests/test_gpu_reference.py — never by the product path.
+
+Recipe: torch.utils.cpp_extension.load on the five files of each variant with
+`-include cstdint` (gcc 13 no longer provides uint32_t/uintptr_t transitively to rasterizer_impl.h:24,40-61) and the
+vendored GLM on the include path.  The tracer needs the OptiX runtime (libnvoptix.so.1), which the GPU boxes of this pool
+do not ship (probed 2026-09-24: `OSError: libnvoptix.so.1: cannot open shared object file`), so it is not built.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+REF = "/root/reference/submodules/diff-surfel-rasterizations"
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+VARIANTS = {
+    "ref_rast_wet": "diff-surfel-rasterization-wet",            # NUM_CHANNELS 3, in-kernel SH
+    "ref_rast_wet_ch05": "diff-surfel-rasterization-wet-ch05",  # NUM_CHANNELS 5 (what EnvGS imports)
+}
+
+
+def build(verbose: bool = False) -> dict:
+    if not os.path.isdir(REF):
+        raise FileNotFoundError(f"{REF} not present (the reference only exists in the build container)")
+    os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0a")
+    os.environ.setdefault("MAX_JOBS", "8")
+    from torch.utils import cpp_extension
+    built = {}
+    for name, sub in VARIANTS.items():
+        src = os.path.join(REF, sub)
+        bdir = os.path.join(OUT, name)
+        os.makedirs(bdir, exist_ok=True)
+        so = os.path.join(bdir, name + ".so")
+        if os.path.exists(so):
+            built[name] = so
+            continue
+        sources = [os.path.join(src, "cuda_rasterizer", f) for f in ("rasterizer_impl.cu", "forward.cu", "backward.cu")]
+        sources += [os.path.join(src, "rasterize_points.cu"), os.path.join(src, "ext.cpp")]
+        cpp_extension.load(
+            name=name, sources=sources, extra_include_paths=[os.path.join(REF, "third_party", "glm"), src],
+            extra_cflags=["-include", "cstdint", "-O3"],
+            extra_cuda_cflags=["-include", "cstdint", "-O3", "-gencode", "arch=compute_100a,code=sm_100a"],
+            build_directory=bdir, verbose=verbose, is_python_module=False)
+        built[name] = so
+    return built
+
+
+def load(name: str):
+    """Import a previously built reference module (GPU box: prebuilt files only, nothing is compiled there)."""
+    import importlib.util
+    import torch  # noqa: F401  (the extension links against libtorch)
+    so = os.path.join(OUT, name, name + ".so")
+    if not os.path.exists(so):
+        raise FileNotFoundError(so)
+    spec = importlib.util.spec_from_file_location(name, so)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+if __name__ == "__main__":
+    print(build(verbose="--verbose" in sys.argv))
