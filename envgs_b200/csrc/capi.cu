@@ -48,14 +48,16 @@ int raster_forward_dispatch(const envgs_raster_args& a, const envgs_raster_out& 
 int raster_backward_dispatch(const envgs_raster_args& a, const int* radii, int R, void* geom, void* binning, void* img,
                              const envgs_raster_grads& gr, cudaStream_t stream);
 int mark_visible_impl(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t stream);
-int trace_forward_impl(Lbvh& bvh, unsigned int* counter, const envgs_trace_args& a, const envgs_trace_out& o, cudaStream_t stream);
-int trace_backward_impl(Lbvh& bvh, unsigned int* counter, const envgs_trace_args& a, const envgs_trace_grads& g, cudaStream_t stream);
+int trace_forward_impl(Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_out& o, cudaStream_t stream);
+int trace_backward_impl(Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_grads& g, cudaStream_t stream);
 
 }  // namespace envgs
 
 struct envgs_tracer {
     envgs::Lbvh bvh;
-    unsigned int* counter = nullptr;
+    unsigned int* counter = nullptr;       // [0]: persistent-warp work counter; stats live 64 bytes further
+    bool stats_on = false;
+    unsigned long long* stats() { return stats_on ? reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(counter) + 64) : nullptr; }
 };
 
 using namespace envgs;
@@ -160,7 +162,7 @@ size_t envgs_raster_binning_bytes(int32_t n) { return BinningState::carve(nullpt
 envgs_tracer* envgs_tracer_create(void) {
     envgs_tracer* h = new (std::nothrow) envgs_tracer();
     if (!h) { set_error("out of host memory"); return nullptr; }
-    if (cudaMalloc(&h->counter, 256) != cudaSuccess) {
+    if (cudaMalloc(&h->counter, 256) != cudaSuccess || cudaMemset(h->counter, 0, 256) != cudaSuccess) {
         set_error("cudaMalloc failed for the tracer work counter: %s", cudaGetErrorString(cudaGetLastError()));
         delete h;
         return nullptr;
@@ -176,6 +178,15 @@ void envgs_tracer_destroy(envgs_tracer* h) {
 }
 
 size_t envgs_tracer_bvh_bytes(int32_t P) { return lbvh_storage_bytes(P); }
+
+int envgs_debug_trace_stats(envgs_tracer* h, int32_t enable, uint64_t out[8]) {
+    if (!h) { set_error("tracer handle is NULL"); return ENVGS_ERR_INVALID; }
+    ENVGS_CUDA_TRY(cudaDeviceSynchronize());
+    if (out) ENVGS_CUDA_TRY(cudaMemcpy(out, reinterpret_cast<char*>(h->counter) + 64, 64, cudaMemcpyDeviceToHost));
+    ENVGS_CUDA_TRY(cudaMemset(reinterpret_cast<char*>(h->counter) + 64, 0, 64));
+    h->stats_on = enable != 0;
+    return ENVGS_OK;
+}
 
 int envgs_tracer_build(envgs_tracer* h, const float* vertices, int32_t num_vertices, int32_t rebuild, envgs_alloc_fn alloc,
                        void* alloc_user, void* stream) {
@@ -235,7 +246,7 @@ int envgs_trace_forward(envgs_tracer* h, const envgs_trace_args* args, const env
         return ENVGS_ERR_INVALID;
     }
     if (args->training && !out->a_weights) { set_error("a_weights is NULL although training is set"); return ENVGS_ERR_INVALID; }
-    return trace_forward_impl(h->bvh, h->counter, *args, *out, (cudaStream_t)stream);
+    return trace_forward_impl(h->bvh, h->counter, h->stats(), *args, *out, (cudaStream_t)stream);
 }
 
 int envgs_trace_backward(envgs_tracer* h, const envgs_trace_args* args, const envgs_trace_grads* g, void* stream) {
@@ -249,7 +260,7 @@ int envgs_trace_backward(envgs_tracer* h, const envgs_trace_args* args, const en
     }
     if (args->shs && !g->dL_dshs) { set_error("dL_dshs is NULL although shs were given"); return ENVGS_ERR_INVALID; }
     if (args->others_precomp && !g->dL_dothers) { set_error("dL_dothers is NULL although others_precomp was given"); return ENVGS_ERR_INVALID; }
-    return trace_backward_impl(h->bvh, h->counter, *args, *g, (cudaStream_t)stream);
+    return trace_backward_impl(h->bvh, h->counter, h->stats(), *args, *g, (cudaStream_t)stream);
 }
 
 }  // extern "C"

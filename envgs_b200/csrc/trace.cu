@@ -25,6 +25,7 @@ struct TraceParams {
     envgs_trace_out o;
     envgs_trace_grads g;
     unsigned int* work_counter;
+    unsigned long long* stats;   // optional debug counters: [rays, nodes, prim tests, hits inserted, chunks, contributions]
     int n_items;      // warp work items
     int tiles_x;      // 8x4 tiles per row (0 => linear mapping)
 };
@@ -33,6 +34,7 @@ struct HitBuf {
     float t[TR_CHUNK];
     int id[TR_CHUNK];
     int cnt;
+    int n_nodes, n_prims;   // debug statistics
 };
 
 __device__ __forceinline__ void hit_insert(HitBuf& hb, float t, int id) {
@@ -59,6 +61,7 @@ __device__ __forceinline__ void prim_test(const QuadPrim* __restrict__ prims, in
     const float4 pv = __ldg(&prims[sid].v1);
     float3 n = f3(pn.x, pn.y, pn.z);
     float q = dot(n, d);
+    hb.n_prims++;
     if (q == 0.0f) return;
     float3 v1 = f3(pv.x, pv.y, pv.z);
     float t = dot(n, v1 - o) / q;
@@ -79,6 +82,7 @@ __device__ __forceinline__ void gather_chunk(const BvhNode* __restrict__ nodes, 
 #pragma unroll
     for (int i = 0; i < TR_CHUNK; i++) { hb.t[i] = TR_DEPTH_INF; hb.id[i] = 0; }
     hb.cnt = 0;
+    hb.n_nodes = 0; hb.n_prims = 0;
     if (!isfinite(d.x + d.y + d.z + o.x + o.y + o.z)) return;
     const float3 inv = f3(safe_inv(d.x), safe_inv(d.y), safe_inv(d.z));
     int lstack[TR_LSTACK];
@@ -89,6 +93,7 @@ __device__ __forceinline__ void gather_chunk(const BvhNode* __restrict__ nodes, 
         const float4 A = __ldg(&nodes[node].a), B = __ldg(&nodes[node].b), C = __ldg(&nodes[node].c);
         const int c0 = __ldg(&nodes[node].child0), c1 = __ldg(&nodes[node].child1);
         const float bound = hb.t[TR_CHUNK - 1];
+        hb.n_nodes++;
         float tn0, tn1;
         bool h0, h1;
         {
@@ -294,11 +299,13 @@ __global__ void __launch_bounds__(TR_THREADS) trace_kernel(const TraceParams p) 
                 const float3 dirn = normalize3(ray_dt);
                 if (use_sh) sh_basis(a.sh_degree, dirn, basis);
                 float3 dL_ddir_sh = f3(0, 0, 0);   // BWD: accumulated dL/d(normalised dir) through SH
+                unsigned int st_nodes = 0, st_prims = 0, st_hits = 0, st_chunks = 0;
 
                 const int max_chunks = a.P / TR_CHUNK + 2;   // every productive chunk consumes 16 distinct surfels
                 for (int chunk = 0; chunk < max_chunks; chunk++) {
                     HitBuf hb;
                     gather_chunk(p.nodes, p.prims, o_chunk, ray_dt, hb, sstack);
+                    st_nodes += hb.n_nodes; st_prims += hb.n_prims; st_hits += hb.cnt; st_chunks++;
                     // spill the sorted chunk to the (now idle) stack area so the compositing loop can index it
                     const int nh = min(hb.cnt, TR_CHUNK);
 #pragma unroll
@@ -521,6 +528,11 @@ __global__ void __launch_bounds__(TR_THREADS) trace_kernel(const TraceParams p) 
                     payload_dpt = dpt;
                     o_chunk = ray_ot + (payload_dpt + TR_STEP_EPSILON) * ray_dt;
                 }
+                if (p.stats) {
+                    atomicAdd(&p.stats[0], 1ull); atomicAdd(&p.stats[1], (unsigned long long)st_nodes);
+                    atomicAdd(&p.stats[2], (unsigned long long)st_prims); atomicAdd(&p.stats[3], (unsigned long long)st_hits);
+                    atomicAdd(&p.stats[4], (unsigned long long)st_chunks); atomicAdd(&p.stats[5], (unsigned long long)contributor);
+                }
                 if (BWD) {
                     if (use_sh) g_ray_d += dnormvdv(ray_dt, dL_ddir_sh);   // backward.cu:182-184
                     continue;
@@ -569,7 +581,7 @@ __global__ void __launch_bounds__(TR_THREADS) trace_kernel(const TraceParams p) 
     }
 }
 
-static int launch_trace(bool bwd, Lbvh& bvh, unsigned int* counter, const envgs_trace_args& a, const envgs_trace_out* o,
+static int launch_trace(bool bwd, Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_out* o,
                         const envgs_trace_grads* g, cudaStream_t stream) {
     static int sm_count = 0, occ_f = 0, occ_b = 0;
     if (sm_count == 0) {
@@ -586,6 +598,7 @@ static int launch_trace(bool bwd, Lbvh& bvh, unsigned int* counter, const envgs_
     if (o) p.o = *o; else memset(&p.o, 0, sizeof(p.o));
     if (g) p.g = *g; else memset(&p.g, 0, sizeof(p.g));
     p.work_counter = counter;
+    p.stats = stats;
     if (a.H >= 4) {
         p.tiles_x = (a.W + 7) / 8;
         p.n_items = p.tiles_x * ((a.H + 3) / 4);
@@ -604,11 +617,11 @@ static int launch_trace(bool bwd, Lbvh& bvh, unsigned int* counter, const envgs_
     return ENVGS_OK;
 }
 
-int trace_forward_impl(Lbvh& bvh, unsigned int* counter, const envgs_trace_args& a, const envgs_trace_out& o, cudaStream_t stream) {
-    return launch_trace(false, bvh, counter, a, &o, nullptr, stream);
+int trace_forward_impl(Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_out& o, cudaStream_t stream) {
+    return launch_trace(false, bvh, counter, stats, a, &o, nullptr, stream);
 }
-int trace_backward_impl(Lbvh& bvh, unsigned int* counter, const envgs_trace_args& a, const envgs_trace_grads& g, cudaStream_t stream) {
-    return launch_trace(true, bvh, counter, a, nullptr, &g, stream);
+int trace_backward_impl(Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_grads& g, cudaStream_t stream) {
+    return launch_trace(true, bvh, counter, stats, a, nullptr, &g, stream);
 }
 
 }  // namespace envgs
