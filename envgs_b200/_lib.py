@@ -53,7 +53,7 @@ class TraceArgs(C.Structure):
 
 class TraceOut(C.Structure):
     _fields_ = [("out_rgb", _fp), ("out_dpt", _fp), ("out_acc", _fp), ("out_norm", _fp), ("out_dist", _fp),
-                ("out_aux", _fp), ("mid_val", _fp), ("a_weights", _fp)]
+                ("out_aux", _fp), ("mid_val", _fp), ("a_weights", _fp), ("hit_cache", _fp)]
 
 
 class TraceGrads(C.Structure):
@@ -62,7 +62,7 @@ class TraceGrads(C.Structure):
         ("mid_val", _fp),
         ("dL_drgb", _fp), ("dL_ddpt", _fp), ("dL_dacc", _fp), ("dL_dnorm", _fp), ("dL_ddist", _fp), ("dL_daux", _fp),
         ("dL_dray_o", _fp), ("dL_dray_d", _fp), ("dL_dmeans3D", _fp), ("dL_dshs", _fp), ("dL_dcolors", _fp),
-        ("dL_dothers", _fp), ("dL_dopacities", _fp), ("dL_dscales", _fp), ("dL_drotations", _fp),
+        ("dL_dothers", _fp), ("dL_dopacities", _fp), ("dL_dscales", _fp), ("dL_drotations", _fp), ("hit_cache", _fp),
     ]
 
 
@@ -71,7 +71,7 @@ EXPORTS = [
     "envgs_last_error", "envgs_version", "envgs_raster_forward", "envgs_raster_backward", "envgs_mark_visible",
     "envgs_raster_geom_bytes", "envgs_raster_img_bytes", "envgs_raster_binning_bytes", "envgs_tracer_create",
     "envgs_tracer_destroy", "envgs_tracer_build", "envgs_tracer_bvh_bytes", "envgs_trace_forward",
-    "envgs_trace_backward", "envgs_launch_count", "envgs_profile_enable", "envgs_profile_report", "envgs_debug_trace_stats",
+    "envgs_trace_backward", "envgs_launch_count", "envgs_profile_enable", "envgs_profile_report", "envgs_debug_trace_stats", "envgs_trace_cache_bytes",
 ]
 
 _lib = None
@@ -116,6 +116,8 @@ def lib() -> C.CDLL:
     L.envgs_profile_enable.argtypes = [C.c_int]
     L.envgs_profile_report.restype = C.c_size_t
     L.envgs_profile_report.argtypes = [C.c_char_p, C.c_size_t]
+    L.envgs_trace_cache_bytes.restype = C.c_size_t
+    L.envgs_trace_cache_bytes.argtypes = [C.c_int32, C.c_int32]
     L.envgs_debug_trace_stats.restype = C.c_int
     L.envgs_debug_trace_stats.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_uint64)]
     _lib = L

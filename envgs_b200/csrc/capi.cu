@@ -50,6 +50,10 @@ int raster_backward_dispatch(const envgs_raster_args& a, const int* radii, int R
 int mark_visible_impl(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t stream);
 int trace_forward_impl(Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_out& o, cudaStream_t stream);
 int trace_backward_impl(Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_grads& g, cudaStream_t stream);
+size_t trace_cache_bytes(int H, int W);
+bool trace_fast_eligible(const envgs_trace_args& a, const void* cache);
+int trace_forward_fast(Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_out& o, void* cache, cudaStream_t stream);
+int trace_backward_fast(Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_grads& g, void* cache, cudaStream_t stream);
 
 }  // namespace envgs
 
@@ -179,6 +183,8 @@ void envgs_tracer_destroy(envgs_tracer* h) {
 
 size_t envgs_tracer_bvh_bytes(int32_t P) { return lbvh_storage_bytes(P); }
 
+size_t envgs_trace_cache_bytes(int32_t H, int32_t W) { return trace_cache_bytes(H, W); }
+
 int envgs_debug_trace_stats(envgs_tracer* h, int32_t enable, uint64_t out[8]) {
     if (!h) { set_error("tracer handle is NULL"); return ENVGS_ERR_INVALID; }
     ENVGS_CUDA_TRY(cudaDeviceSynchronize());
@@ -246,6 +252,8 @@ int envgs_trace_forward(envgs_tracer* h, const envgs_trace_args* args, const env
         return ENVGS_ERR_INVALID;
     }
     if (args->training && !out->a_weights) { set_error("a_weights is NULL although training is set"); return ENVGS_ERR_INVALID; }
+    if (trace_fast_eligible(*args, out->hit_cache))
+        return trace_forward_fast(h->bvh, h->counter, h->stats(), *args, *out, out->hit_cache, (cudaStream_t)stream);
     return trace_forward_impl(h->bvh, h->counter, h->stats(), *args, *out, (cudaStream_t)stream);
 }
 
@@ -260,6 +268,8 @@ int envgs_trace_backward(envgs_tracer* h, const envgs_trace_args* args, const en
     }
     if (args->shs && !g->dL_dshs) { set_error("dL_dshs is NULL although shs were given"); return ENVGS_ERR_INVALID; }
     if (args->others_precomp && !g->dL_dothers) { set_error("dL_dothers is NULL although others_precomp was given"); return ENVGS_ERR_INVALID; }
+    if (trace_fast_eligible(*args, g->hit_cache))
+        return trace_backward_fast(h->bvh, h->counter, h->stats(), *args, *g, g->hit_cache, (cudaStream_t)stream);
     return trace_backward_impl(h->bvh, h->counter, h->stats(), *args, *g, (cudaStream_t)stream);
 }
 

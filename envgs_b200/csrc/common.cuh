@@ -191,6 +191,26 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// Warp "transpose-reduce": every lane holds NV (<= 32) partial values v[0..NV-1] (v[i] = 0 for i >= NV); after the
+// call lane l holds the warp-wide sum of v[l].  31 shuffles in 5 dependent stages instead of 5*NV for NV separate
+// butterfly sums — the reduction step of render_bwd (one atomic per lane afterwards).
+template <int NV>
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane) {
+#pragma unroll
+    for (int i = NV; i < 32; i++) v[i] = 0.0f;
+#pragma unroll
+    for (int h = 16; h >= 1; h >>= 1) {
+        const bool up = (lane & h) != 0;
+#pragma unroll
+        for (int i = 0; i < h; i++) {
+            const float send = up ? v[i] : v[i + h];
+            const float keep = up ? v[i + h] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+        }
+    }
+    return v[0];
+}
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 }  // namespace envgs

@@ -108,10 +108,10 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(
             const float4 r0 = s_r0[j], r1 = s_r1[j], r2 = s_r2[j];
             const float3 Tu = f3(r0.x, r0.y, r0.z), Tv = f3(r0.w, r1.x, r1.y), Tw = f3(r1.z, r1.w, r2.x);
 
-            float g[NG];
+            float g[32];
 #pragma unroll
-            for (int q = 0; q < NG; q++) g[q] = 0.0f;
-            bool contrib = false, branch3d = false;
+            for (int q = 0; q < 32; q++) g[q] = 0.0f;
+            bool contrib = false;
 
             if (pos <= last_contributor) {
                 float3 k = pxf * Tw - Tu;
@@ -174,7 +174,6 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(
                             dL_dz += w * dL_ddepth;
                             g[C + 3] = G * dL_dalpha;
                             if (rho3d <= rho2d) {
-                                branch3d = true;
                                 const float dLdsx = dL_dG * -G * sx + dL_dz * Tw.x;
                                 const float dLdsy = dL_dG * -G * sy + dL_dz * Tw.y;
                                 const float dsx_pz = dLdsx / p.z, dsy_pz = dLdsy / p.z;
@@ -197,34 +196,10 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(
                     }
                 }
             }
-            const unsigned any_c = __ballot_sync(0xffffffffu, contrib);
-            if (any_c == 0) continue;
-            const bool any3d = __any_sync(0xffffffffu, branch3d);
-            const bool any2d = __any_sync(0xffffffffu, contrib && !branch3d);
-            float* sg = s_g + j * NG;
-#pragma unroll
-            for (int q = 0; q < C + 4; q++) {
-                float v = warp_sum(g[q]);
-                if (lane == 0) atomicAdd(&sg[q], v);
-            }
-            if (any3d) {
-#pragma unroll
-                for (int q = C + 4; q < C + 12; q++) {
-                    float v = warp_sum(g[q]);
-                    if (lane == 0) atomicAdd(&sg[q], v);
-                }
-            }
-            {
-                float v = warp_sum(g[C + 12]);
-                if (lane == 0) atomicAdd(&sg[C + 12], v);
-            }
-            if (any2d) {
-#pragma unroll
-                for (int q = C + 13; q < C + 15; q++) {
-                    float v = warp_sum(g[q]);
-                    if (lane == 0) atomicAdd(&sg[q], v);
-                }
-            }
+            if (!__any_sync(0xffffffffu, contrib)) continue;
+            // warp -> CTA reduction: transpose-reduce (lane q ends up with the warp sum of component q), one shared atomic per lane
+            const float tot = warp_transpose_reduce<NG>(g, lane);
+            if (lane < NG && tot != 0.0f) atomicAdd(&s_g[j * NG + lane], tot);
         }
         __syncthreads();
         // flush this batch: thread t owns surfel slot t

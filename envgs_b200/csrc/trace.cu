@@ -28,6 +28,8 @@ struct TraceParams {
     unsigned long long* stats;   // optional debug counters: [rays, nodes, prim tests, hits inserted, chunks, contributions]
     int n_items;      // warp work items
     int tiles_x;      // 8x4 tiles per row (0 => linear mapping)
+    const int* ray_list;             // optional: trace only these rays (overflow fallback of the fast path) ...
+    const unsigned int* ray_count;   // ... whose number lives on the device
 };
 
 struct HitBuf {
@@ -187,16 +189,25 @@ __global__ void __launch_bounds__(TR_THREADS) trace_kernel(const TraceParams p) 
         unsigned int item = 0;
         if (lane == 0) item = atomicAdd(p.work_counter, 1u);
         item = __shfl_sync(0xffffffffu, item, 0);
-        if (item >= (unsigned)p.n_items) break;
         int row, col;
-        if (p.tiles_x > 0) {
+        bool listed = true;
+        if (p.ray_list != nullptr) {
+            const unsigned int n = *p.ray_count;
+            if (item >= (n + 31u) / 32u) break;
+            const unsigned int k = item * 32u + lane;
+            listed = k < n;
+            const int r = listed ? p.ray_list[k] : 0;
+            row = r / W; col = r % W;
+        } else if (p.tiles_x > 0) {
+            if (item >= (unsigned)p.n_items) break;
             int by = item / p.tiles_x, bx = item % p.tiles_x;
             row = by * 4 + (lane >> 3); col = bx * 8 + (lane & 7);
         } else {
+            if (item >= (unsigned)p.n_items) break;
             long long r = (long long)item * 32 + lane;
             row = (int)(r / W); col = (int)(r % W);
         }
-        const bool active = row < H && col < W;
+        const bool active = listed && row < H && col < W;
         if (active) {
             const size_t tidx = (size_t)row * W + col;
             const float3 ray_o0 = ld3(a.ray_o, (int)tidx), ray_d0 = ld3(a.ray_d, (int)tidx);
@@ -581,8 +592,8 @@ __global__ void __launch_bounds__(TR_THREADS) trace_kernel(const TraceParams p) 
     }
 }
 
-static int launch_trace(bool bwd, Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_out* o,
-                        const envgs_trace_grads* g, cudaStream_t stream) {
+int launch_trace(bool bwd, Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_out* o,
+                 const envgs_trace_grads* g, const int* ray_list, const unsigned int* ray_count, cudaStream_t stream) {
     static int sm_count = 0, occ_f = 0, occ_b = 0;
     if (sm_count == 0) {
         int dev = 0;
@@ -599,6 +610,8 @@ static int launch_trace(bool bwd, Lbvh& bvh, unsigned int* counter, unsigned lon
     if (g) p.g = *g; else memset(&p.g, 0, sizeof(p.g));
     p.work_counter = counter;
     p.stats = stats;
+    p.ray_list = ray_list;
+    p.ray_count = ray_count;
     if (a.H >= 4) {
         p.tiles_x = (a.W + 7) / 8;
         p.n_items = p.tiles_x * ((a.H + 3) / 4);
@@ -610,7 +623,8 @@ static int launch_trace(bool bwd, Lbvh& bvh, unsigned int* counter, unsigned lon
     int blocks = sm_count * (bwd ? occ_b : occ_f);
     int need = (p.n_items + (TR_THREADS / 32) - 1) / (TR_THREADS / 32);
     if (blocks > need) blocks = need > 0 ? need : 1;
-    ENVGS_TIMED(bwd ? "trace_bwd" : "trace_fwd", stream);
+    if (ray_list != nullptr) blocks = sm_count;   // count is only known on the device; idle CTAs exit at once
+    ENVGS_TIMED(ray_list ? (bwd ? "trace_bwd_fallback" : "trace_fwd_fallback") : (bwd ? "trace_bwd" : "trace_fwd"), stream);
     if (bwd) trace_kernel<true><<<blocks, TR_THREADS, 0, stream>>>(p);
     else trace_kernel<false><<<blocks, TR_THREADS, 0, stream>>>(p);
     ENVGS_LAUNCH_CHECK(bwd ? "trace_bwd" : "trace_fwd", false, stream);
@@ -618,10 +632,10 @@ static int launch_trace(bool bwd, Lbvh& bvh, unsigned int* counter, unsigned lon
 }
 
 int trace_forward_impl(Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_out& o, cudaStream_t stream) {
-    return launch_trace(false, bvh, counter, stats, a, &o, nullptr, stream);
+    return launch_trace(false, bvh, counter, stats, a, &o, nullptr, nullptr, nullptr, stream);
 }
 int trace_backward_impl(Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_grads& g, cudaStream_t stream) {
-    return launch_trace(true, bvh, counter, stats, a, nullptr, &g, stream);
+    return launch_trace(true, bvh, counter, stats, a, nullptr, &g, nullptr, nullptr, stream);
 }
 
 }  // namespace envgs

@@ -1,0 +1,582 @@
+// trace_fast.cu — the tracer's fast path for EnvGS' own call shape (max_trace_depth = 0, start_from_first = false):
+//
+//   traverse_kernel   one ray per lane, persistent warps over 8x4 pixel blocks, "while-while" LBVH traversal
+//                     (inner loop over internal nodes, inner loop over leaves) with the per-lane stack and hit list in
+//                     shared memory.  Finds ALL quad hits of the ray; a ray with more than 15 hits is handed to the
+//                     monolithic kernel of trace.cu (which implements the reference's 16-hit chunk restart exactly).
+//                     Hits are rank-sorted by distance straight into HBM: hits[ray][16] (t, surfel) = one 128-byte line.
+//   shade_fwd_kernel  HIT-parallel: a half-warp (16 lanes) per ray, one hit per lane.  Per-hit evaluation (surfel
+//                     frame, alpha, SH colour) runs in parallel; the front-to-back recurrence T_i = T_{i-1}(1-a_i) is a
+//                     4-step segmented shuffle scan; every accumulated output is one transpose-reduce.
+//   shade_bwd_kernel  same layout; the reference's suffix terms (F - F_i)/(1-a_i) come from inclusive scans.  It re-uses
+//                     the forward's hit lists, so the backward pass does no BVH traversal at all.
+//
+// Semantics are those of TRACE/optix_tracer/forward.cu:219-450 and backward.cu:508-887 for a ray whose first 16-hit
+// chunk is not full (payload.cnt < CHUNK_SIZE => the while loop ends after one optixTrace, forward.cu:434).
+#include "lbvh.cuh"
+
+namespace envgs {
+
+constexpr int TF_THREADS = 128;
+constexpr int TF_STACK = 32;
+constexpr int TF_LSTACK = 64;
+constexpr int TF_MAXHITS = 16;               // list capacity; a usable list has at most 15 entries
+constexpr int STACK_EMPTY = (int)0x80000000;
+
+struct FastParams {
+    const BvhNode* nodes;
+    const QuadPrim* prims;
+    envgs_trace_args a;
+    envgs_trace_out o;
+    envgs_trace_grads g;
+    float2* hits;                 // [R][16] (t, surfel id as int bits)
+    int* counts;                  // [R] number of hits, -1 = overflow (handled by the fallback kernel)
+    unsigned int* overflow_count; // [1]
+    int* overflow_list;           // [R]
+    unsigned int* work_counter;
+    unsigned long long* stats;
+    int n_items, tiles_x;
+};
+
+size_t trace_cache_bytes(int H, int W) {
+    size_t R = (size_t)H * W;
+    return R * (TF_MAXHITS * sizeof(float2) + 4 + 4) + 1024;
+}
+static void carve_cache(char* base, int H, int W, FastParams& p) {
+    size_t R = (size_t)H * W;
+    p.hits = reinterpret_cast<float2*>(base);
+    p.counts = reinterpret_cast<int*>(base + R * TF_MAXHITS * sizeof(float2));
+    p.overflow_list = p.counts + R;
+    p.overflow_count = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(p.overflow_list + R) + 256);
+}
+
+__device__ __forceinline__ float safe_inv_f(float d) { return 1.0f / (fabsf(d) > 1e-30f ? d : copysignf(1e-30f, d)); }
+
+// ------------------------------------------------------------------------------------------------------
+// traversal
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TF_THREADS) traverse_kernel(const FastParams p) {
+    __shared__ int s_stack[TF_STACK * TF_THREADS];
+    __shared__ float s_ht[TF_MAXHITS * TF_THREADS];
+    __shared__ int s_hid[TF_MAXHITS * TF_THREADS];
+    const int lane = threadIdx.x & 31;
+    int* sstack = s_stack + threadIdx.x;
+    float* ht = s_ht + threadIdx.x;
+    int* hid = s_hid + threadIdx.x;
+    const int H = p.a.H, W = p.a.W;
+    const BvhNode* __restrict__ nodes = p.nodes;
+    const QuadPrim* __restrict__ prims = p.prims;
+
+    while (true) {
+        unsigned int item = 0;
+        if (lane == 0) item = atomicAdd(p.work_counter, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= (unsigned)p.n_items) break;
+        int row, col;
+        if (p.tiles_x > 0) {
+            int by = item / p.tiles_x, bx = item % p.tiles_x;
+            row = by * 4 + (lane >> 3); col = bx * 8 + (lane & 7);
+        } else {
+            long long r = (long long)item * 32 + lane;
+            row = (int)(r / W); col = (int)(r % W);
+        }
+        const bool active = row < H && col < W;
+        const size_t ray = active ? (size_t)row * W + col : 0;
+        float3 o = f3(0, 0, 0), d = f3(0, 0, 0);
+        if (active) { o = ld3(p.a.ray_o, (int)ray); d = ld3(p.a.ray_d, (int)ray); }
+        const bool finite = isfinite(d.x + d.y + d.z + o.x + o.y + o.z);
+        const float3 inv = f3(safe_inv_f(d.x), safe_inv_f(d.y), safe_inv_f(d.z));
+        int cnt = 0;
+        bool overflow = false;
+        unsigned int st_nodes = 0, st_prims = 0;
+        int lstack[TF_LSTACK];
+        int sp = 0;
+        int node = (active && finite) ? 0 : STACK_EMPTY;
+
+        while (node != STACK_EMPTY) {
+            // ---- internal nodes ----
+            while (node >= 0) {
+                const float4 A = __ldg(&nodes[node].a), B = __ldg(&nodes[node].b), C = __ldg(&nodes[node].c);
+                const int c0 = __ldg(&nodes[node].child0), c1 = __ldg(&nodes[node].child1);
+                st_nodes++;
+                bool h0, h1;
+                {
+                    float ax = (A.x - o.x) * inv.x, bx = (A.w - o.x) * inv.x;
+                    float ay = (A.y - o.y) * inv.y, by = (B.x - o.y) * inv.y;
+                    float az = (A.z - o.z) * inv.z, bz = (B.y - o.z) * inv.z;
+                    float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+                    float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) * 1.0000004f;
+                    h0 = (tn <= tf) && (tf > 0.0f);
+                }
+                {
+                    float ax = (B.z - o.x) * inv.x, bx = (C.y - o.x) * inv.x;
+                    float ay = (B.w - o.y) * inv.y, by = (C.z - o.y) * inv.y;
+                    float az = (C.x - o.z) * inv.z, bz = (C.w - o.z) * inv.z;
+                    float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+                    float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) * 1.0000004f;
+                    h1 = (tn <= tf) && (tf > 0.0f);
+                }
+                if (h0 && h1) {
+                    if (sp < TF_STACK) sstack[sp * TF_THREADS] = c1;
+                    else if (sp < TF_STACK + TF_LSTACK) lstack[sp - TF_STACK] = c1;
+                    sp = min(sp + 1, TF_STACK + TF_LSTACK);
+                    node = c0;
+                } else if (h0) {
+                    node = c0;
+                } else if (h1) {
+                    node = c1;
+                } else {
+                    if (sp == 0) { node = STACK_EMPTY; break; }
+                    sp--;
+                    node = (sp < TF_STACK) ? sstack[sp * TF_THREADS] : lstack[sp - TF_STACK];
+                }
+            }
+            // ---- leaves ----
+            while (node < 0 && node != STACK_EMPTY) {
+                const int sid = ~node;
+                st_prims++;
+                const float4 pn = __ldg(&prims[sid].n);
+                const float4 pv = __ldg(&prims[sid].v1);
+                const float3 n = f3(pn.x, pn.y, pn.z);
+                const float q = dot(n, d);
+                if (q != 0.0f) {
+                    const float3 v1 = f3(pv.x, pv.y, pv.z);
+                    const float t = dot(n, v1 - o) / q;
+                    if (t > 0.0f && t < TR_DEPTH_INF) {
+                        const float4 pu = __ldg(&prims[sid].eu);
+                        const float4 pw = __ldg(&prims[sid].ev);
+                        const float3 r = (o + t * d) - v1;
+                        const float a = dot(r, f3(pu.x, pu.y, pu.z)) * pv.w;
+                        const float b = dot(r, f3(pw.x, pw.y, pw.z)) * pu.w;
+                        if (pw.w != 0.0f && a >= 0.0f && a <= 1.0f && b >= 0.0f && b <= 1.0f) {
+                            if (cnt < TF_MAXHITS) { ht[cnt * TF_THREADS] = t; hid[cnt * TF_THREADS] = sid; }
+                            cnt++;
+                            if (cnt >= TF_MAXHITS) { overflow = true; sp = 0; }   // full chunk: the fallback kernel takes this ray
+                        }
+                    }
+                }
+                if (sp == 0) { node = STACK_EMPTY; break; }
+                sp--;
+                node = (sp < TF_STACK) ? sstack[sp * TF_THREADS] : lstack[sp - TF_STACK];
+            }
+        }
+
+        if (active) {
+            if (overflow) {
+                p.counts[ray] = -1;
+                const unsigned int k = atomicAdd(p.overflow_count, 1u);
+                p.overflow_list[k] = (int)ray;
+            } else {
+                p.counts[ray] = cnt;
+                float2* out = p.hits + ray * TF_MAXHITS;
+                for (int i = 0; i < cnt; i++) {   // rank sort straight into the output line
+                    const float ti = ht[i * TF_THREADS];
+                    int rank = 0;
+                    for (int j = 0; j < cnt; j++) {
+                        const float tj = ht[j * TF_THREADS];
+                        rank += (tj < ti || (tj == ti && j < i)) ? 1 : 0;
+                    }
+                    out[rank] = make_float2(ti, __int_as_float(hid[i * TF_THREADS]));
+                }
+            }
+            if (p.stats) {
+                atomicAdd(&p.stats[0], 1ull); atomicAdd(&p.stats[1], (unsigned long long)st_nodes);
+                atomicAdd(&p.stats[2], (unsigned long long)st_prims); atomicAdd(&p.stats[3], (unsigned long long)cnt);
+                atomicAdd(&p.stats[4], 1ull);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// hit-parallel shading helpers (16 lanes per ray)
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float seg_scan_mul(float v, int h) {   // inclusive product over the half-warp
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+        float u = __shfl_up_sync(0xffffffffu, v, o, 16);
+        if (h >= o) v *= u;
+    }
+    return v;
+}
+__device__ __forceinline__ float seg_scan_add(float v, int h) {   // inclusive sum over the half-warp
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+        float u = __shfl_up_sync(0xffffffffu, v, o, 16);
+        if (h >= o) v += u;
+    }
+    return v;
+}
+// transpose-reduce inside a half-warp: lane h ends up with the sum over the 16 lanes of v[h]
+__device__ __forceinline__ float half_transpose_reduce(float (&v)[16], int h) {
+#pragma unroll
+    for (int s = 8; s >= 1; s >>= 1) {
+        const bool up = (h & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; i++) {
+            const float send = up ? v[i] : v[i + s];
+            const float keep = up ? v[i + s] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s, 16);
+        }
+    }
+    return v[0];
+}
+
+struct HitEval {
+    bool contrib;          // passes every test and lies before the termination point
+    float alpha, G, w, T_prev, cmd, opac;
+    float3 normal;         // flipped world-space normal
+    float nsign;
+    float2 uv, scale;
+    float4 rot;
+    float3 mu, tu, tv, xyz, c;
+    bool clamped[3];
+    float oth[2];
+    int gidx;
+};
+
+// Evaluate this lane's hit and run the transmittance scan.  Returns T_final (same for the 16 lanes).
+__device__ __forceinline__ float eval_and_scan(const envgs_trace_args& a, bool valid, float tmx, int gidx, float3 ray_o, float3 ray_d,
+                                               const float* __restrict__ basis, int nbasis, bool sh_vec4, float3 campos, int h,
+                                               HitEval& e) {
+    e.gidx = gidx;
+    bool cand = valid;
+    e.alpha = 0.0f; e.G = 0.0f; e.cmd = 1.0f; e.opac = 0.0f; e.nsign = 1.0f;
+    e.normal = f3(0, 0, 0); e.c = f3(0, 0, 0); e.oth[0] = e.oth[1] = 0.0f;
+    e.clamped[0] = e.clamped[1] = e.clamped[2] = false;
+    e.uv = make_float2(0, 0); e.scale = make_float2(1, 1); e.rot = make_float4(1, 0, 0, 0);
+    e.mu = e.tu = e.tv = e.xyz = f3(0, 0, 0);
+    if (valid) {
+        const float dpt = tmx;   // first chunk: payload.dpt == 0 (forward.cu:300)
+        e.xyz = ray_o + dpt * ray_d;
+        e.mu = ld3(a.means3D, gidx);
+        e.scale = reinterpret_cast<const float2*>(a.scales)[gidx];
+        e.rot = reinterpret_cast<const float4*>(a.rotations)[gidx];
+        Rot3 R = quat_to_rot(e.rot);
+        e.tu = R.c0; e.tv = R.c1;
+        const float3 nr = R.c2;
+        const float Tx = dot(e.tu, e.mu), Ty = dot(e.tv, e.mu);
+        const float u1 = e.tu.x * e.xyz.x + e.tu.y * e.xyz.y + e.tu.z * e.xyz.z + (-Tx);
+        const float v1 = e.tv.x * e.xyz.x + e.tv.y * e.xyz.y + e.tv.z * e.xyz.z + (-Ty);
+        e.uv = make_float2(u1 / e.scale.x, v1 / e.scale.y);
+        const float rho3d = e.uv.x * e.uv.x + e.uv.y * e.uv.y;
+        const float cosv = -sum3((e.mu - campos) * nr);
+        if (cosv == 0.0f) cand = false;
+        e.nsign = cosv > 0.0f ? 1.0f : -1.0f;
+        e.normal = e.nsign * nr;
+        e.cmd = dpt;
+        if (e.cmd < TR_START_OFFSET) cand = false;
+        const float power = -0.5f * rho3d;
+        if (power > 0.0f) cand = false;
+        e.opac = a.opacities[gidx];
+        e.G = expf(power);
+        e.alpha = fminf(0.99f, e.opac * e.G);
+        if (e.alpha < 1.0f / 255.0f) cand = false;
+    }
+    const float one_m = cand ? 1.0f - e.alpha : 1.0f;
+    const float T_incl = seg_scan_mul(one_m, h);
+    float T_excl = __shfl_up_sync(0xffffffffu, T_incl, 1, 16);
+    if (h == 0) T_excl = 1.0f;
+    // termination: the first candidate whose T_next drops below 1e-4 and everything behind it are dropped (forward.cu:370-372)
+    const unsigned int half_shift = (threadIdx.x & 16);
+    const unsigned int stop_mask = (__ballot_sync(0xffffffffu, cand && (T_incl < 0.0001f)) >> half_shift) & 0xffffu;
+    const int stop = stop_mask ? (__ffs(stop_mask) - 1) : 16;
+    e.contrib = cand && h < stop;
+    e.T_prev = T_excl;
+    e.w = e.contrib ? e.alpha * T_excl : 0.0f;
+    // final transmittance = product over contributors = inclusive product at the last lane before `stop`
+    const int last = stop - 1;
+    float T_final = __shfl_sync(0xffffffffu, T_incl, last < 0 ? 0 : last, 16);
+    if (last < 0) T_final = 1.0f;
+
+    if (e.contrib) {   // colour and auxiliaries only where they are used
+        if (a.colors_precomp == nullptr) {
+            const float* sh = a.shs + (size_t)gidx * a.sh_coeffs * 3;
+            float3 res = f3(0, 0, 0);
+            if (sh_vec4) {
+                const float4* s4 = reinterpret_cast<const float4*>(sh);
+                float tmp[48];
+#pragma unroll
+                for (int q = 0; q < 12; q++) {
+                    if (q * 4 < nbasis * 3) { float4 v = __ldg(&s4[q]); tmp[4 * q] = v.x; tmp[4 * q + 1] = v.y; tmp[4 * q + 2] = v.z; tmp[4 * q + 3] = v.w; }
+                    else { tmp[4 * q] = tmp[4 * q + 1] = tmp[4 * q + 2] = tmp[4 * q + 3] = 0.0f; }
+                }
+#pragma unroll
+                for (int k = 0; k < 16; k++)
+                    if (k < nbasis) res += basis[k] * f3(tmp[3 * k], tmp[3 * k + 1], tmp[3 * k + 2]);
+            } else {
+                for (int k = 0; k < nbasis; k++) res += basis[k] * f3(sh[3 * k], sh[3 * k + 1], sh[3 * k + 2]);
+            }
+            res.x += 0.5f; res.y += 0.5f; res.z += 0.5f;
+            e.clamped[0] = res.x < 0; e.clamped[1] = res.y < 0; e.clamped[2] = res.z < 0;
+            e.c = f3(fmaxf(res.x, 0.0f), fmaxf(res.y, 0.0f), fmaxf(res.z, 0.0f));
+        } else {
+            e.c = ld3(a.colors_precomp, gidx);
+        }
+        if (a.others_precomp != nullptr) {
+            e.oth[0] = a.others_precomp[2 * (size_t)gidx];
+            e.oth[1] = a.others_precomp[2 * (size_t)gidx + 1];
+        }
+    }
+    return T_final;
+}
+
+constexpr int SH_RAYS_PER_BLOCK = 16;   // 256 threads
+
+__global__ void __launch_bounds__(256) shade_fwd_kernel(const FastParams p, int R) {
+    const envgs_trace_args& a = p.a;
+    const int h = threadIdx.x & 15;
+    const long long ray_ll = (long long)blockIdx.x * SH_RAYS_PER_BLOCK + (threadIdx.x >> 4);
+    const bool ray_ok = ray_ll < R;
+    const size_t ray = ray_ok ? (size_t)ray_ll : 0;
+    const int cnt = ray_ok ? p.counts[ray] : -1;
+    const bool live = cnt >= 0;                 // -1: overflow ray, written by the fallback kernel
+    const float3 campos = f3(a.campos[0], a.campos[1], a.campos[2]);
+    const int nbasis = (a.sh_degree + 1) * (a.sh_degree + 1);
+    const bool use_sh = a.colors_precomp == nullptr;
+    const bool sh_vec4 = use_sh && ((a.sh_coeffs * 3) % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.shs) & 15) == 0);
+
+    const float3 ray_o = ld3(a.ray_o, (int)ray), ray_d = ld3(a.ray_d, (int)ray);
+    float basis[16];
+    if (use_sh) sh_basis(a.sh_degree, normalize3(ray_d), basis);
+    const bool valid = live && h < cnt;
+    float2 hit = make_float2(0.0f, 0.0f);
+    if (valid) hit = p.hits[ray * TF_MAXHITS + h];
+    HitEval e;
+    const float T_final = eval_and_scan(a, valid, hit.x, __float_as_int(hit.y), ray_o, ray_d, basis, nbasis, sh_vec4, campos, h, e);
+
+    // distortion bookkeeping needs exclusive prefix sums of w*m and w*m^2 (forward.cu:405-409)
+    const float m = FAR_N / (FAR_N - NEAR_N) * (1.0f - NEAR_N / e.cmd);
+    const float wm = e.w * m, wmm = e.w * m * m;
+    const float M1_ex = seg_scan_add(wm, h) - wm, M2_ex = seg_scan_add(wmm, h) - wmm;
+    float v[16];
+    v[0] = e.w * (m * m * (1.0f - e.T_prev) + M2_ex - 2.0f * m * M1_ex);
+    v[1] = wm; v[2] = wmm; v[3] = 0.0f; v[4] = 0.0f; v[5] = 0.0f;
+    v[6] = e.w * e.cmd; v[7] = 0.0f;
+    v[8] = e.w * e.normal.x; v[9] = e.w * e.normal.y; v[10] = e.w * e.normal.z;
+    v[11] = e.w * e.oth[0]; v[12] = e.w * e.oth[1];
+    v[13] = e.w * e.c.x; v[14] = e.w * e.c.y; v[15] = e.w * e.c.z;
+    const float tot = half_transpose_reduce(v, h);   // lane h: sum of component h (mid_val layout for h >= 6)
+
+    if (live) {
+        if (a.training && e.contrib) atomicAdd(&p.o.a_weights[e.gidx], e.w);
+        // lane h owns mid_val[h] (config.h:18-26): 0-2 ray_o, 3-5 ray_d, 6 D, 7 A, 8-10 N, 11-12 aux, 13-15 rgb (+ T*bg)
+        float mv;
+        if (h < 3) mv = h == 0 ? ray_o.x : (h == 1 ? ray_o.y : ray_o.z);
+        else if (h < 6) mv = h == 3 ? ray_d.x : (h == 4 ? ray_d.y : ray_d.z);
+        else if (h == 7) mv = 1.0f - T_final;
+        else if (h >= 13) mv = tot + T_final * a.background[h - 13];
+        else mv = tot;
+        float* mid = p.o.mid_val + ray * 32;
+        mid[h] = mv;
+        mid[16 + h] = 0.0f;
+        if (h < 3) p.o.out_dist[ray * 3 + h] = tot;                 // dist, M1, M2
+        else if (h == 6) p.o.out_dpt[ray] = mv;
+        else if (h == 7) p.o.out_acc[ray] = mv;
+        else if (h >= 8 && h <= 10) p.o.out_norm[ray * 3 + (h - 8)] = mv;
+        else if (h == 11 || h == 12) p.o.out_aux[ray * 2 + (h - 11)] = mv;
+        else if (h >= 13) p.o.out_rgb[ray * 3 + (h - 13)] = mv;     // max_trace_depth == 0: f_this = s_prod = 1
+    }
+}
+
+__global__ void __launch_bounds__(256) shade_bwd_kernel(const FastParams p, int R) {
+    const envgs_trace_args& a = p.a;
+    const envgs_trace_grads& g = p.g;
+    const int h = threadIdx.x & 15;
+    const long long ray_ll = (long long)blockIdx.x * SH_RAYS_PER_BLOCK + (threadIdx.x >> 4);
+    const bool ray_ok = ray_ll < R;
+    const size_t ray = ray_ok ? (size_t)ray_ll : 0;
+    const int cnt = ray_ok ? p.counts[ray] : -1;
+    const float3 campos = f3(a.campos[0], a.campos[1], a.campos[2]);
+    const int nbasis = (a.sh_degree + 1) * (a.sh_degree + 1);
+    const bool use_sh = a.colors_precomp == nullptr;
+    const bool sh_vec4 = use_sh && ((a.sh_coeffs * 3) % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.shs) & 15) == 0);
+
+    // saved forward state of the (only) segment
+    const float* mid = g.mid_val + ray * 32;
+    const float3 ray_o = f3(mid[MID_RAYO], mid[MID_RAYO + 1], mid[MID_RAYO + 2]);
+    const float3 ray_d = f3(mid[MID_RAYD], mid[MID_RAYD + 1], mid[MID_RAYD + 2]);
+    // backward.cu:952-957 with i = 0: s_prev = 1
+    const bool live = cnt >= 0 && !(length3(ray_d) == 0.0f || 1.0f <= a.specular_threshold);
+    const float seg_rgb[3] = {mid[MID_RGB], mid[MID_RGB + 1], mid[MID_RGB + 2]};
+    const float seg_dpt = mid[MID_DPT], seg_acc = mid[MID_ACC];
+    const float3 seg_norm = f3(mid[MID_NORM], mid[MID_NORM + 1], mid[MID_NORM + 2]);
+    const float seg_aux[2] = {mid[MID_AUX], mid[MID_AUX + 1]};
+    const float dL_drgb[3] = {g.dL_drgb[ray * 3], g.dL_drgb[ray * 3 + 1], g.dL_drgb[ray * 3 + 2]};
+    const float dL_ddpt = g.dL_ddpt[ray];
+    const float3 dL_dnorm = ld3(g.dL_dnorm, (int)ray);
+    const float dL_daux[2] = {g.dL_daux[ray * 2], g.dL_daux[ray * 2 + 1]};
+    const float T_final_saved = 1.0f - seg_acc;
+
+    float basis[16];
+    const float3 dirn = normalize3(ray_d);
+    if (use_sh) sh_basis(a.sh_degree, dirn, basis);
+    const bool valid = live && h < cnt;
+    float2 hit = make_float2(0.0f, 0.0f);
+    if (valid) hit = p.hits[ray * TF_MAXHITS + h];
+    HitEval e;
+    eval_and_scan(a, valid, hit.x, __float_as_int(hit.y), ray_o, ray_d, basis, nbasis, sh_vec4, campos, h, e);
+
+    // inclusive prefix sums the reference keeps in C, O, D, N while walking front to back
+    const float Cx = seg_scan_add(e.w * e.c.x, h), Cy = seg_scan_add(e.w * e.c.y, h), Cz = seg_scan_add(e.w * e.c.z, h);
+    const float O0 = seg_scan_add(e.w * e.oth[0], h), O1 = seg_scan_add(e.w * e.oth[1], h);
+    const float Dp = seg_scan_add(e.w * e.cmd, h);
+    const float Nx = seg_scan_add(e.w * e.normal.x, h), Ny = seg_scan_add(e.w * e.normal.y, h), Nz = seg_scan_add(e.w * e.normal.z, h);
+
+    float3 g_ray_o = f3(0, 0, 0), g_ray_d = f3(0, 0, 0), dL_ddir_sh = f3(0, 0, 0);
+    if (e.contrib) {
+        const int gidx = e.gidx;
+        const float alpha = e.alpha, T_prev = e.T_prev, w = e.w, G = e.G, cmd = e.cmd;
+        const float cc[3] = {e.c.x, e.c.y, e.c.z}, Cc[3] = {Cx, Cy, Cz}, O[2] = {O0, O1};
+        float dL_dalpha = 0.0f;
+        float dL_dcolor[3];
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+            dL_dcolor[ch] = dL_drgb[ch] * w;
+            dL_dalpha += dL_drgb[ch] * (T_prev * cc[ch] - (seg_rgb[ch] - Cc[ch]) / (1.0f - alpha));
+            dL_dalpha += dL_drgb[ch] * a.background[ch] * (-T_final_saved / (1.0f - alpha));
+        }
+        if (a.others_precomp != nullptr) {
+#pragma unroll
+            for (int ch = 0; ch < 2; ch++) {
+                atomicAdd(&g.dL_dothers[2 * (size_t)gidx + ch], dL_daux[ch] * w);
+                dL_dalpha += dL_daux[ch] * (T_prev * e.oth[ch] - (seg_aux[ch] - O[ch]) / (1.0f - alpha));
+            }
+        }
+        const float dL_dD = dL_ddpt * w;
+        dL_dalpha += dL_ddpt * (T_prev * cmd - (seg_dpt - Dp) / (1.0f - alpha));
+        const float3 dL_dN = dL_dnorm * w;
+        dL_dalpha += sum3(dL_dnorm * (T_prev * e.normal - (seg_norm - f3(Nx, Ny, Nz)) / (1.0f - alpha)));
+        const float dL_dG = dL_dalpha * e.opac;
+        atomicAdd(&g.dL_dopacities[gidx], dL_dalpha * G);
+
+        // compute_transmat_uv_backward (backward.cu:233-335), plane form t = m.(mu-o)/(m.d), m = t_u x t_v
+        const float2 dL_duv = make_float2(dL_dG * -G * e.uv.x, dL_dG * -G * e.uv.y);
+        const float3 xm = e.xyz - e.mu;
+        float3 dR0 = (dL_duv.x / e.scale.x) * xm;
+        float3 dR1 = (dL_duv.y / e.scale.y) * xm;
+        const float3 dR2 = e.nsign * dL_dN;
+        const float2 dL_dscale = make_float2(dL_dG * (G * e.uv.x * e.uv.x / e.scale.x), dL_dG * (G * e.uv.y * e.uv.y / e.scale.y));
+        float3 dL_dmean = dL_dG * (G * ((e.uv.x / e.scale.x) * e.tu + (e.uv.y / e.scale.y) * e.tv));
+        const float3 dL_dxyz = (dL_duv.x / e.scale.x) * e.tu + (dL_duv.y / e.scale.y) * e.tv;
+        const float dL_dd = dL_dD + dot(dL_dxyz, ray_d);
+        const float3 mvec = cross(e.tu, e.tv);
+        const float qd = dot(mvec, ray_d);
+        const float3 cvec = e.mu - ray_o;
+        const float pn = dot(mvec, cvec);
+        const float3 dt_dm = (cvec - (pn / qd) * ray_d) / qd;
+        dR0 += dL_dd * cross(e.tv, dt_dm);
+        dR1 += dL_dd * cross(dt_dm, e.tu);
+        dL_dmean += dL_dd * (mvec / qd);
+        g_ray_o = dL_dxyz + dL_dd * (-(mvec / qd));
+        g_ray_d = dL_dxyz * cmd + dL_dd * (-pn / (qd * qd)) * mvec;
+        Rot3 gR; gR.c0 = dR0; gR.c1 = dR1; gR.c2 = dR2;
+        const float4 dL_drot = quat_to_rot_vjp(e.rot, gR);
+
+        atomicAdd(&g.dL_dscales[2 * (size_t)gidx + 0], dL_dscale.x);
+        atomicAdd(&g.dL_dscales[2 * (size_t)gidx + 1], dL_dscale.y);
+        atomicAdd(&g.dL_drotations[4 * (size_t)gidx + 0], dL_drot.x);
+        atomicAdd(&g.dL_drotations[4 * (size_t)gidx + 1], dL_drot.y);
+        atomicAdd(&g.dL_drotations[4 * (size_t)gidx + 2], dL_drot.z);
+        atomicAdd(&g.dL_drotations[4 * (size_t)gidx + 3], dL_drot.w);
+        atomicAdd(&g.dL_dmeans3D[3 * (size_t)gidx + 0], dL_dmean.x);
+        atomicAdd(&g.dL_dmeans3D[3 * (size_t)gidx + 1], dL_dmean.y);
+        atomicAdd(&g.dL_dmeans3D[3 * (size_t)gidx + 2], dL_dmean.z);
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) atomicAdd(&g.dL_dcolors[3 * (size_t)gidx + ch], dL_dcolor[ch]);
+        if (use_sh) {
+            const float3 dRGB = f3(e.clamped[0] ? 0.0f : dL_dcolor[0], e.clamped[1] ? 0.0f : dL_dcolor[1], e.clamped[2] ? 0.0f : dL_dcolor[2]);
+            float* dsh = g.dL_dshs + (size_t)gidx * a.sh_coeffs * 3;
+            for (int k = 0; k < nbasis; k++) {
+                atomicAdd(&dsh[3 * k + 0], basis[k] * dRGB.x);
+                atomicAdd(&dsh[3 * k + 1], basis[k] * dRGB.y);
+                atomicAdd(&dsh[3 * k + 2], basis[k] * dRGB.z);
+            }
+            float3 gx, gy, gz;
+            sh_dir_grad(a.sh_degree, dirn, a.shs + (size_t)gidx * a.sh_coeffs * 3, gx, gy, gz);
+            dL_ddir_sh = f3(dot(gx, dRGB), dot(gy, dRGB), dot(gz, dRGB));
+        }
+    }
+    // per-ray gradients: sum over the 16 hits
+    float v[16];
+    v[0] = g_ray_o.x; v[1] = g_ray_o.y; v[2] = g_ray_o.z; v[3] = g_ray_d.x; v[4] = g_ray_d.y; v[5] = g_ray_d.z;
+    v[6] = dL_ddir_sh.x; v[7] = dL_ddir_sh.y; v[8] = dL_ddir_sh.z;
+#pragma unroll
+    for (int i = 9; i < 16; i++) v[i] = 0.0f;
+    const float tot = half_transpose_reduce(v, h);
+    const float sx = __shfl_sync(0xffffffffu, tot, 6, 16), sy = __shfl_sync(0xffffffffu, tot, 7, 16), sz = __shfl_sync(0xffffffffu, tot, 8, 16);
+    if (ray_ok && cnt >= 0) {   // overflow rays (cnt < 0) are written by the fallback kernel
+        float3 extra = f3(0, 0, 0);
+        if (use_sh && live) extra = dnormvdv(ray_d, f3(sx, sy, sz));   // backward.cu:182-184
+        if (h < 3) g.dL_dray_o[ray * 3 + h] = live ? tot : 0.0f;
+        else if (h < 6) g.dL_dray_d[ray * 3 + (h - 3)] = live ? tot + (h == 3 ? extra.x : (h == 4 ? extra.y : extra.z)) : 0.0f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------
+int launch_trace(bool bwd, Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_out* o,
+                 const envgs_trace_grads* g, const int* ray_list, const unsigned int* ray_count, cudaStream_t stream);
+
+bool trace_fast_eligible(const envgs_trace_args& a, const void* cache) {
+    if (cache == nullptr || a.max_trace_depth != 0 || a.start_from_first != 0) return false;
+    const char* f = getenv("ENVGS_TRACE_FORCE_MONOLITHIC");
+    return !(f && f[0] == '1');
+}
+
+int trace_forward_fast(Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_out& o,
+                       void* cache, cudaStream_t stream) {
+    static int sm_count = 0, occ = 0;
+    if (sm_count == 0) {
+        int dev = 0;
+        ENVGS_CUDA_TRY(cudaGetDevice(&dev));
+        ENVGS_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+        ENVGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, traverse_kernel, TF_THREADS, 0));
+        if (occ < 1) occ = 1;
+    }
+    FastParams p;
+    memset(&p, 0, sizeof(p));
+    p.nodes = bvh.nodes; p.prims = bvh.prims; p.a = a; p.o = o;
+    carve_cache((char*)cache, a.H, a.W, p);
+    p.work_counter = counter;
+    p.stats = stats;
+    if (a.H >= 4) { p.tiles_x = (a.W + 7) / 8; p.n_items = p.tiles_x * ((a.H + 3) / 4); }
+    else { p.tiles_x = 0; p.n_items = (int)(((long long)a.H * a.W + 31) / 32); }
+    const int R = a.H * a.W;
+    ENVGS_CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream));
+    ENVGS_CUDA_TRY(cudaMemsetAsync(p.overflow_count, 0, sizeof(unsigned int), stream));
+    int blocks = sm_count * occ;
+    int need = (p.n_items + (TF_THREADS / 32) - 1) / (TF_THREADS / 32);
+    if (blocks > need) blocks = need > 0 ? need : 1;
+    {
+        ENVGS_TIMED("trace_traverse", stream);
+        traverse_kernel<<<blocks, TF_THREADS, 0, stream>>>(p);
+        ENVGS_LAUNCH_CHECK("trace_traverse", false, stream);
+    }
+    {
+        ENVGS_TIMED("trace_shade_fwd", stream);
+        shade_fwd_kernel<<<(R + SH_RAYS_PER_BLOCK - 1) / SH_RAYS_PER_BLOCK, 256, 0, stream>>>(p, R);
+        ENVGS_LAUNCH_CHECK("trace_shade_fwd", false, stream);
+    }
+    // rays whose first chunk was full: the reference's multi-chunk loop, run by the monolithic kernel on the device-side list
+    return launch_trace(false, bvh, counter, stats, a, &o, nullptr, p.overflow_list, p.overflow_count, stream);
+}
+
+int trace_backward_fast(Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_grads& g,
+                        void* cache, cudaStream_t stream) {
+    FastParams p;
+    memset(&p, 0, sizeof(p));
+    p.nodes = bvh.nodes; p.prims = bvh.prims; p.a = a; p.g = g;
+    carve_cache((char*)cache, a.H, a.W, p);
+    const int R = a.H * a.W;
+    {
+        ENVGS_TIMED("trace_shade_bwd", stream);
+        shade_bwd_kernel<<<(R + SH_RAYS_PER_BLOCK - 1) / SH_RAYS_PER_BLOCK, 256, 0, stream>>>(p, R);
+        ENVGS_LAUNCH_CHECK("trace_shade_bwd", false, stream);
+    }
+    return launch_trace(true, bvh, counter, stats, a, nullptr, &g, p.overflow_list, p.overflow_count, stream);
+}
+
+}  // namespace envgs

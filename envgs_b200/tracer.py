@@ -137,10 +137,15 @@ class _TraceSurfels(torch.autograd.Function):
         out_norm, out_dist, out_aux = torch.zeros((H, W, 3), **f), torch.zeros((H, W, 3), **f), torch.zeros((H, W, AUX_CHANNELS), **f)
         mid_val = torch.empty((H, W, MID_CHANNELS * (MAX_TRACE_DEPTH + 1)), **f)   # fully written by the kernel
         a_weights = torch.zeros((P, 1), **f) if training else None
+        # scratch for the hit-parallel fast path (per-ray hit lists, re-used by backward); the library falls back to the
+        # general kernel when the call shape is not eligible
+        hit_cache = None
+        if int(s.max_trace_depth) == 0 and not start_from_first:
+            hit_cache = torch.empty(int(L.envgs_trace_cache_bytes(H, W)), dtype=torch.uint8, device=device)
 
         args = _trace_args(P, H, W, s, training, start_from_first, ro, rd, bg, m3, sh, col, oth, opa, sc, rot, vm, pm, cam)
         out = _lib.TraceOut(_lib.ptr(out_rgb), _lib.ptr(out_dpt), _lib.ptr(out_acc), _lib.ptr(out_norm), _lib.ptr(out_dist),
-                            _lib.ptr(out_aux), _lib.ptr(mid_val), _lib.ptr(a_weights))
+                            _lib.ptr(out_aux), _lib.ptr(mid_val), _lib.ptr(a_weights), _lib.ptr(hit_cache))
         stream = torch.cuda.current_stream(device).cuda_stream
 
         def run():
@@ -166,6 +171,7 @@ class _TraceSurfels(torch.autograd.Function):
         ctx.optix_context = optix_context
         ctx.start_from_first = start_from_first
         ctx.bg = bg
+        ctx.hit_cache = hit_cache
         ctx.save_for_backward(ro, rd, m3, sh, col, oth, opa, sc, rot, out_rgb, out_dpt, out_acc, out_norm, out_dist,
                               out_aux, mid_val)
         acc_wet = a_weights if a_weights is not None else torch.zeros_like(means3D[:, 0])
@@ -201,7 +207,8 @@ class _TraceSurfels(torch.autograd.Function):
             _lib.ptr(out_rgb), _lib.ptr(out_dpt), _lib.ptr(out_acc), _lib.ptr(out_norm), _lib.ptr(out_dist), _lib.ptr(out_aux),
             _lib.ptr(mid_val), _lib.ptr(g_rgb), _lib.ptr(g_dpt), _lib.ptr(g_acc), _lib.ptr(g_norm), _lib.ptr(g_dist),
             _lib.ptr(g_aux), _lib.ptr(dL_dray_o), _lib.ptr(dL_dray_d), _lib.ptr(dL_dmeans3D), _lib.ptr(dL_dshs),
-            _lib.ptr(dL_dcolors), _lib.ptr(dL_dothers), _lib.ptr(dL_dopacities), _lib.ptr(dL_dscales), _lib.ptr(dL_drotations))
+            _lib.ptr(dL_dcolors), _lib.ptr(dL_dothers), _lib.ptr(dL_dopacities), _lib.ptr(dL_dscales), _lib.ptr(dL_drotations),
+            _lib.ptr(ctx.hit_cache))
         stream = torch.cuda.current_stream(device).cuda_stream
 
         def run():

@@ -164,9 +164,14 @@ typedef struct envgs_trace_out {   /* all written for every ray; a_weights accum
     float* out_norm;  /* (H,W,3)  */
     float* out_dist;  /* (H,W,3)  [distortion, M1, M2] */
     float* out_aux;   /* (H,W,2)  */
-    float* mid_val;   /* (H,W,32) zero-filled by caller */
+    float* mid_val;   /* (H,W,32) fully written */
     float* a_weights; /* (P,1) or NULL when !training */
+    void* hit_cache;  /* optional scratch of envgs_trace_cache_bytes(H,W) bytes: enables the hit-parallel fast path for
+                         max_trace_depth == 0 && !start_from_first and carries the per-ray hit lists to the backward call;
+                         NULL selects the general (monolithic) kernel */
 } envgs_trace_out;
+
+size_t envgs_trace_cache_bytes(int32_t H, int32_t W);
 
 int envgs_trace_forward(envgs_tracer* h, const envgs_trace_args* args, const envgs_trace_out* out, void* stream);
 
@@ -191,6 +196,7 @@ typedef struct envgs_trace_grads {
     float* dL_dopacities;  /* (P,1) */
     float* dL_dscales;     /* (P,2) */
     float* dL_drotations;  /* (P,4) */
+    void* hit_cache;       /* the buffer the forward call filled, or NULL */
 } envgs_trace_grads;
 
 int envgs_trace_backward(envgs_tracer* h, const envgs_trace_args* args, const envgs_trace_grads* grads,
