@@ -131,9 +131,9 @@ int envgs_raster_forward(const envgs_raster_args* args, const envgs_raster_out* 
                          envgs_alloc_fn binning_alloc, envgs_alloc_fn img_alloc, void* alloc_user, void* stream) {
     int rc = check_raster_args(args);
     if (rc != ENVGS_OK) return rc;
+    if (args->P == 0) return 0;   // reference leaves the zero-filled outputs untouched (rasterize_points.cu:100)
     if (!out || !out->out_color || !out->out_others || !out->out_weight) { set_error("output pointer is NULL"); return ENVGS_ERR_INVALID; }
     if (!geom_alloc || !binning_alloc || !img_alloc) { set_error("allocator callback is NULL"); return ENVGS_ERR_INVALID; }
-    if (args->P == 0) return 0;   // reference leaves the zero-filled outputs untouched (rasterize_points.cu:100)
     return raster_forward_dispatch(*args, *out, geom_alloc, binning_alloc, img_alloc, alloc_user, (cudaStream_t)stream);
 }
 

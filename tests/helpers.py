@@ -91,7 +91,8 @@ def run_oracle_raster(base, cam, C, feats=None, use_sh=False, bg=None, g_color=N
     if g_color is not None:
         loss = (res.color * g_color.to(dtype)).sum() + (res.allmap * g_others.to(dtype)).sum()
         loss.backward()
-        out.update(g_means=means.grad.float(), g_opac=opac.grad.float(),
+        gz = lambda t: torch.zeros_like(t).float() if t.grad is None else t.grad.float()
+        out.update(g_means=gz(means), g_opac=gz(opac),
                    g_means2D=RO.densify_signal(res, cam.tanfovx, cam.tanfovy, cam.W, cam.H).float())
         if transmat is None:
             out.update(g_scales=scales.grad.float(), g_rots=rots.grad.float())
@@ -105,8 +106,23 @@ def run_oracle_raster(base, cam, C, feats=None, use_sh=False, bg=None, g_color=N
 
 
 def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
-    a, b = a.double(), b.double()
+    a, b = a.detach().double(), b.detach().double()
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def trimmed_rel_l2(a: torch.Tensor, b: torch.Tensor, frac: float = 2e-3, min_drop: int = 2) -> float:
+    """Relative L2 error over surfels after dropping the `frac` of surfels with the largest error.
+
+    Per-surfel gradients of nearly edge-on / sub-pixel surfels are ill-conditioned in fp32: the fp32 oracle differs from
+    the fp64 oracle on exactly those surfels by the same amount the fp32 kernels do ("tolerances"), and a
+    single such surfel can dominate the global L2 norm.  The norm in the denominator is the FULL reference norm."""
+    a, b = a.detach().double(), b.detach().double()
+    d = (a - b).reshape(a.shape[0], -1).norm(dim=1)
+    k = max(min_drop, int(frac * d.numel()))
+    keep = torch.ones_like(d, dtype=torch.bool)
+    if d.numel() > k:
+        keep[d.topk(k).indices] = False
+    return float((d[keep] ** 2).sum().sqrt() / b.norm().clamp_min(1e-30))
 
 
 def frac_above(a: torch.Tensor, b: torch.Tensor, tol: float) -> float:
@@ -179,7 +195,7 @@ def run_cuda_trace(env, cam, ray_o, ray_d, *, use_sh=True, others=False, start_f
 
 
 def run_oracle_trace(env, cam, ray_o, ray_d, *, use_sh=True, others=False, start_from_first=False, max_trace_depth=0,
-                     specular_threshold=0.0, grads=None, dtype=torch.float64, bg=None):
+                     specular_threshold=0.0, grads=None, dtype=torch.float64, bg=None, max_hits=96, ray_chunk=2048):
     bg = torch.zeros(3) if bg is None else bg
     leaf = lambda t: t.to(dtype).clone().requires_grad_(True)
     means, opac, scales, rots = leaf(env.means), leaf(env.opacities), leaf(env.scales), leaf(env.rotations)
@@ -193,7 +209,7 @@ def run_oracle_trace(env, cam, ray_o, ray_d, *, use_sh=True, others=False, start
         oth = leaf(torch.cat([env.specular, env.roughness], -1))
     res = TO.trace(ro, rd, means, opac, scales, rots, shs=shs, colors_precomp=colors, others_precomp=oth, sh_degree=3,
                    campos=cam.campos, bg=bg, start_from_first=start_from_first, max_trace_depth=max_trace_depth,
-                   specular_threshold=specular_threshold, projmatrix=cam.projmatrix)
+                   specular_threshold=specular_threshold, projmatrix=cam.projmatrix, max_hits=max_hits, ray_chunk=ray_chunk)
     out = dict(rgb=res.rgb.detach().float(), dpt=res.dpt.detach().float(), acc=res.acc.detach().float(),
                norm=res.norm.detach().float(), dist=res.dist.detach().float(), aux=res.aux.detach().float(),
                mid=res.mid.float(), wet=res.wet.detach().float())

@@ -1,0 +1,86 @@
+"""CPU: the C-ABI library builds for sm_100a without a GPU, loads, exports every symbol include/envgs_b200.h declares,
+and reports errors through return codes + envgs_last_error (no compute calls here)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "envgs_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(envgs_[a-z_0-9]+)\s*\(", text)) - {"envgs_alloc_fn"})
+
+
+def test_header_symbols_are_exported(built_lib):
+    from envgs_b200 import _lib
+    L = _lib.lib()
+    declared = _declared_symbols()
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/envgs_b200.h but not exported"
+    assert sorted(_lib.EXPORTS) == declared
+    assert L.envgs_version() >= 100
+
+
+def test_only_sm100a_code_is_embedded(built_lib):
+    import subprocess
+    out = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "--list-elf", built_lib], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_size_queries_and_error_reporting(built_lib):
+    from envgs_b200 import _lib
+    L = _lib.lib()
+    assert L.envgs_raster_geom_bytes(1000) > 1000 * 64
+    assert L.envgs_raster_img_bytes(1920, 1080) >= 1920 * 1080 * 20
+    assert L.envgs_raster_binning_bytes(0) > 0
+    assert L.envgs_tracer_bvh_bytes(262144) > 262144 * 128
+    assert L.envgs_trace_cache_bytes(1080, 1920) >= 1080 * 1920 * 136
+    args = _lib.RasterArgs()
+    args.P, args.C, args.width, args.height = 10, 4, 64, 64          # unsupported channel count
+    out = _lib.RasterOut()
+    cb = _lib.ALLOC_FN(lambda u, n: None)
+    rc = L.envgs_raster_forward(C.byref(args), C.byref(out), cb, cb, cb, None, None)
+    assert rc == -1 and b"channel" in L.envgs_last_error()
+    args.C = 5                                                          # non-RGB without precomputed colours
+    rc = L.envgs_raster_forward(C.byref(args), C.byref(out), cb, cb, cb, None, None)
+    assert rc == -1
+    with pytest.raises(RuntimeError):
+        _lib.check(rc, "envgs_raster_forward")
+    assert L.envgs_trace_forward(None, None, None, None) == -1
+
+
+def test_drop_in_packages_expose_reference_names(built_lib):
+    import diff_surfel_rasterization_wet as w3
+    import diff_surfel_rasterization_wet_ch05 as w5
+    import diff_surfel_rasterization_wet_ch07 as w7
+    import diff_surfel_tracing as tr
+    assert (w3.NUM_CHANNELS, w5.NUM_CHANNELS, w7.NUM_CHANNELS) == (3, 5, 7)
+    for m in (w3, w5, w7):
+        assert m.GaussianRasterizationSettings._fields == ("image_height", "image_width", "tanfovx", "tanfovy", "bg",
+                                                           "scale_modifier", "viewmatrix", "projmatrix", "sh_degree", "campos",
+                                                           "prefiltered", "debug")
+        assert hasattr(m.GaussianRasterizer, "markVisible") and hasattr(m, "rasterize_gaussians")
+    assert tr.SurfelTracingSettings._fields[-2:] == ("max_trace_depth", "specular_threshold")
+    import inspect
+    sig = inspect.signature(tr.SurfelTracer.forward)
+    assert list(sig.parameters)[1:6] == ["ray_o", "ray_d", "vertices", "means3D", "grads3D"]
+    assert sig.parameters["start_from_first"].default is True
+    sig = inspect.signature(w5.GaussianRasterizer.forward)
+    assert list(sig.parameters)[1:] == ["means3D", "means2D", "opacities", "shs", "colors_precomp", "scales", "rotations", "cov3D_precomp"]
+
+
+def test_product_path_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "envgs_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "import oracle" not in src and "from oracle" not in src, fn
+    for d in ("diff_surfel_rasterization_wet", "diff_surfel_rasterization_wet_ch05", "diff_surfel_rasterization_wet_ch07", "diff_surfel_tracing"):
+        src = open(os.path.join(ROOT, d, "__init__.py")).read()
+        assert "oracle" not in src

@@ -49,7 +49,7 @@ def test_dense_scene_many_chunks(built_lib):
     ro, rd = Hh.synthetic_rays(24, 32, seed=6)
     up = _up(24, 32, 30)
     cu = Hh.run_cuda_trace(env, cam, ro, rd, grads=up)
-    orc = Hh.run_oracle_trace(env, cam, ro, rd, grads=up)
+    orc = Hh.run_oracle_trace(env, cam, ro, rd, grads=up, max_hits=1024, ray_chunk=256)
     _check(cu, orc, ["g_means", "g_opac", "g_scales", "g_rots", "g_shs", "g_ray_d"], frac_tol=3e-3, grad_tol=2e-3)
 
 
