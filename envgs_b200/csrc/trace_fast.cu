@@ -36,6 +36,7 @@ struct FastParams {
     unsigned int* work_counter;
     unsigned long long* stats;
     int n_items, tiles_x;
+    int refill_threshold;         // leave an inner traversal loop when fewer lanes than this are still in it
 };
 
 size_t trace_cache_bytes(int H, int W) {
@@ -55,137 +56,150 @@ __device__ __forceinline__ float safe_inv_f(float d) { return 1.0f / (fabsf(d) >
 // ------------------------------------------------------------------------------------------------------
 // traversal
 // ------------------------------------------------------------------------------------------------------
+// Persistent warps with LANE-level work refill: a lane whose ray has finished immediately takes the next ray from a
+// global cursor (warp-aggregated atomic), so a warp never idles behind its longest ray — reflection rays off a noisy
+// normal map are incoherent and their traversal lengths differ by an order of magnitude.  Ray k maps to pixel
+// (8x4 block k/32, position k%32), so rays fetched together are still neighbours on screen.  Hits are appended
+// unsorted to the ray's own 128-byte line in HBM/L2 (the shading kernels sort the 16 slots with a bitonic network).
+__device__ __forceinline__ bool ray_of_index(const FastParams& p, unsigned int k, int& row, int& col) {
+    const int H = p.a.H, W = p.a.W;
+    if (p.tiles_x > 0) {
+        const unsigned int item = k >> 5, l = k & 31;
+        const int by = item / p.tiles_x, bx = item % p.tiles_x;
+        row = by * 4 + (int)(l >> 3); col = bx * 8 + (int)(l & 7);
+    } else {
+        row = (int)(k / (unsigned)W); col = (int)(k % (unsigned)W);
+    }
+    return row < H && col < W;
+}
+
 __global__ void __launch_bounds__(TF_THREADS) traverse_kernel(const FastParams p) {
     __shared__ int s_stack[TF_STACK * TF_THREADS];
-    __shared__ float s_ht[TF_MAXHITS * TF_THREADS];
-    __shared__ int s_hid[TF_MAXHITS * TF_THREADS];
     const int lane = threadIdx.x & 31;
     int* sstack = s_stack + threadIdx.x;
-    float* ht = s_ht + threadIdx.x;
-    int* hid = s_hid + threadIdx.x;
-    const int H = p.a.H, W = p.a.W;
+    const int W = p.a.W;
     const BvhNode* __restrict__ nodes = p.nodes;
     const QuadPrim* __restrict__ prims = p.prims;
+    const unsigned int total = (unsigned int)p.n_items * 32u;   // ray slots (tiles are padded to 32)
+
+    int node = STACK_EMPTY;        // STACK_EMPTY <=> this lane has no ray in flight
+    bool have_ray = false, exhausted = false;
+    size_t ray = 0;
+    float3 o = f3(0, 0, 0), d = f3(0, 0, 1), inv = f3(0, 0, 0);
+    int cnt = 0, sp = 0;
+    bool overflow = false;
+    unsigned int st_nodes = 0, st_prims = 0;
+    int lstack[TF_LSTACK];
 
     while (true) {
-        unsigned int item = 0;
-        if (lane == 0) item = atomicAdd(p.work_counter, 1u);
-        item = __shfl_sync(0xffffffffu, item, 0);
-        if (item >= (unsigned)p.n_items) break;
-        int row, col;
-        if (p.tiles_x > 0) {
-            int by = item / p.tiles_x, bx = item % p.tiles_x;
-            row = by * 4 + (lane >> 3); col = bx * 8 + (lane & 7);
-        } else {
-            long long r = (long long)item * 32 + lane;
-            row = (int)(r / W); col = (int)(r % W);
-        }
-        const bool active = row < H && col < W;
-        const size_t ray = active ? (size_t)row * W + col : 0;
-        float3 o = f3(0, 0, 0), d = f3(0, 0, 0);
-        if (active) { o = ld3(p.a.ray_o, (int)ray); d = ld3(p.a.ray_d, (int)ray); }
-        const bool finite = isfinite(d.x + d.y + d.z + o.x + o.y + o.z);
-        const float3 inv = f3(safe_inv_f(d.x), safe_inv_f(d.y), safe_inv_f(d.z));
-        int cnt = 0;
-        bool overflow = false;
-        unsigned int st_nodes = 0, st_prims = 0;
-        int lstack[TF_LSTACK];
-        int sp = 0;
-        int node = (active && finite) ? 0 : STACK_EMPTY;
-
-        while (node != STACK_EMPTY) {
-            // ---- internal nodes ----
-            while (node >= 0) {
-                const float4 A = __ldg(&nodes[node].a), B = __ldg(&nodes[node].b), C = __ldg(&nodes[node].c);
-                const int c0 = __ldg(&nodes[node].child0), c1 = __ldg(&nodes[node].child1);
-                st_nodes++;
-                bool h0, h1;
-                {
-                    float ax = (A.x - o.x) * inv.x, bx = (A.w - o.x) * inv.x;
-                    float ay = (A.y - o.y) * inv.y, by = (B.x - o.y) * inv.y;
-                    float az = (A.z - o.z) * inv.z, bz = (B.y - o.z) * inv.z;
-                    float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
-                    float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) * 1.0000004f;
-                    h0 = (tn <= tf) && (tf > 0.0f);
-                }
-                {
-                    float ax = (B.z - o.x) * inv.x, bx = (C.y - o.x) * inv.x;
-                    float ay = (B.w - o.y) * inv.y, by = (C.z - o.y) * inv.y;
-                    float az = (C.x - o.z) * inv.z, bz = (C.w - o.z) * inv.z;
-                    float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
-                    float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) * 1.0000004f;
-                    h1 = (tn <= tf) && (tf > 0.0f);
-                }
-                if (h0 && h1) {
-                    if (sp < TF_STACK) sstack[sp * TF_THREADS] = c1;
-                    else if (sp < TF_STACK + TF_LSTACK) lstack[sp - TF_STACK] = c1;
-                    sp = min(sp + 1, TF_STACK + TF_LSTACK);
-                    node = c0;
-                } else if (h0) {
-                    node = c0;
-                } else if (h1) {
-                    node = c1;
-                } else {
-                    if (sp == 0) { node = STACK_EMPTY; break; }
-                    sp--;
-                    node = (sp < TF_STACK) ? sstack[sp * TF_THREADS] : lstack[sp - TF_STACK];
-                }
-            }
-            // ---- leaves ----
-            while (node < 0 && node != STACK_EMPTY) {
-                const int sid = ~node;
-                st_prims++;
-                const float4 pn = __ldg(&prims[sid].n);
-                const float4 pv = __ldg(&prims[sid].v1);
-                const float3 n = f3(pn.x, pn.y, pn.z);
-                const float q = dot(n, d);
-                if (q != 0.0f) {
-                    const float3 v1 = f3(pv.x, pv.y, pv.z);
-                    const float t = dot(n, v1 - o) / q;
-                    if (t > 0.0f && t < TR_DEPTH_INF) {
-                        const float4 pu = __ldg(&prims[sid].eu);
-                        const float4 pw = __ldg(&prims[sid].ev);
-                        const float3 r = (o + t * d) - v1;
-                        const float a = dot(r, f3(pu.x, pu.y, pu.z)) * pv.w;
-                        const float b = dot(r, f3(pw.x, pw.y, pw.z)) * pu.w;
-                        if (pw.w != 0.0f && a >= 0.0f && a <= 1.0f && b >= 0.0f && b <= 1.0f) {
-                            if (cnt < TF_MAXHITS) { ht[cnt * TF_THREADS] = t; hid[cnt * TF_THREADS] = sid; }
-                            cnt++;
-                            if (cnt >= TF_MAXHITS) { overflow = true; sp = 0; }   // full chunk: the fallback kernel takes this ray
-                        }
-                    }
-                }
-                if (sp == 0) { node = STACK_EMPTY; break; }
-                sp--;
-                node = (sp < TF_STACK) ? sstack[sp * TF_THREADS] : lstack[sp - TF_STACK];
-            }
-        }
-
-        if (active) {
+        // ---- retire finished rays, refill idle lanes ----
+        const bool idle = (node == STACK_EMPTY);
+        if (idle && have_ray) {
             if (overflow) {
                 p.counts[ray] = -1;
                 const unsigned int k = atomicAdd(p.overflow_count, 1u);
                 p.overflow_list[k] = (int)ray;
             } else {
                 p.counts[ray] = cnt;
-                float2* out = p.hits + ray * TF_MAXHITS;
-                for (int i = 0; i < cnt; i++) {   // rank sort straight into the output line
-                    const float ti = ht[i * TF_THREADS];
-                    int rank = 0;
-                    for (int j = 0; j < cnt; j++) {
-                        const float tj = ht[j * TF_THREADS];
-                        rank += (tj < ti || (tj == ti && j < i)) ? 1 : 0;
-                    }
-                    out[rank] = make_float2(ti, __int_as_float(hid[i * TF_THREADS]));
-                }
             }
             if (p.stats) {
                 atomicAdd(&p.stats[0], 1ull); atomicAdd(&p.stats[1], (unsigned long long)st_nodes);
                 atomicAdd(&p.stats[2], (unsigned long long)st_prims); atomicAdd(&p.stats[3], (unsigned long long)cnt);
                 atomicAdd(&p.stats[4], 1ull);
             }
+            have_ray = false;
         }
-        __syncwarp();
+        const unsigned int want = __ballot_sync(0xffffffffu, idle && !exhausted);
+        if (want) {
+            const int leader = __ffs(want) - 1;
+            unsigned int base = 0;
+            if (lane == leader) base = atomicAdd(p.work_counter, (unsigned int)__popc(want));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (idle && !exhausted) {
+                unsigned int k = base + __popc(want & ((1u << lane) - 1u));
+                // skip padding slots (pixels outside the image in the last tile column/row)
+                int row = 0, col = 0;
+                bool ok = false;
+                if (k < total) ok = ray_of_index(p, k, row, col);
+                else exhausted = true;
+                if (ok) {
+                    ray = (size_t)row * W + col;
+                    o = ld3(p.a.ray_o, (int)ray); d = ld3(p.a.ray_d, (int)ray);
+                    inv = f3(safe_inv_f(d.x), safe_inv_f(d.y), safe_inv_f(d.z));
+                    cnt = 0; sp = 0; overflow = false; st_nodes = 0; st_prims = 0;
+                    have_ray = true;
+                    node = isfinite(d.x + d.y + d.z + o.x + o.y + o.z) ? 0 : STACK_EMPTY;
+                }
+            }
+        }
+        if (__all_sync(0xffffffffu, exhausted && node == STACK_EMPTY && !have_ray)) break;
+
+        // ---- internal nodes ----
+        while (node >= 0) {
+            const float4 A = __ldg(&nodes[node].a), B = __ldg(&nodes[node].b), C = __ldg(&nodes[node].c);
+            const int c0 = __ldg(&nodes[node].child0), c1 = __ldg(&nodes[node].child1);
+            st_nodes++;
+            bool h0, h1;
+            {
+                float ax = (A.x - o.x) * inv.x, bx = (A.w - o.x) * inv.x;
+                float ay = (A.y - o.y) * inv.y, by = (B.x - o.y) * inv.y;
+                float az = (A.z - o.z) * inv.z, bz = (B.y - o.z) * inv.z;
+                float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+                float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) * 1.0000004f;
+                h0 = (tn <= tf) && (tf > 0.0f);
+            }
+            {
+                float ax = (B.z - o.x) * inv.x, bx = (C.y - o.x) * inv.x;
+                float ay = (B.w - o.y) * inv.y, by = (C.z - o.y) * inv.y;
+                float az = (C.x - o.z) * inv.z, bz = (C.w - o.z) * inv.z;
+                float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+                float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) * 1.0000004f;
+                h1 = (tn <= tf) && (tf > 0.0f);
+            }
+            if (h0 && h1) {
+                if (sp < TF_STACK) sstack[sp * TF_THREADS] = c1;
+                else if (sp < TF_STACK + TF_LSTACK) lstack[sp - TF_STACK] = c1;
+                sp = min(sp + 1, TF_STACK + TF_LSTACK);
+                node = c0;
+            } else if (h0) {
+                node = c0;
+            } else if (h1) {
+                node = c1;
+            } else {
+                if (sp == 0) { node = STACK_EMPTY; break; }
+                sp--;
+                node = (sp < TF_STACK) ? sstack[sp * TF_THREADS] : lstack[sp - TF_STACK];
+            }
+            if (__popc(__activemask()) < p.refill_threshold) break;   // let the idle lanes fetch new rays (Aila & Laine 2009)
+        }
+        // ---- leaves ----
+        while (node < 0 && node != STACK_EMPTY) {
+            const int sid = ~node;
+            st_prims++;
+            const float4 pn = __ldg(&prims[sid].n);
+            const float4 pv = __ldg(&prims[sid].v1);
+            const float3 n = f3(pn.x, pn.y, pn.z);
+            const float q = dot(n, d);
+            if (q != 0.0f) {
+                const float3 v1 = f3(pv.x, pv.y, pv.z);
+                const float t = dot(n, v1 - o) / q;
+                if (t > 0.0f && t < TR_DEPTH_INF) {
+                    const float4 pu = __ldg(&prims[sid].eu);
+                    const float4 pw = __ldg(&prims[sid].ev);
+                    const float3 r = (o + t * d) - v1;
+                    const float a = dot(r, f3(pu.x, pu.y, pu.z)) * pv.w;
+                    const float b = dot(r, f3(pw.x, pw.y, pw.z)) * pu.w;
+                    if (pw.w != 0.0f && a >= 0.0f && a <= 1.0f && b >= 0.0f && b <= 1.0f) {
+                        if (cnt < TF_MAXHITS) p.hits[ray * TF_MAXHITS + cnt] = make_float2(t, __int_as_float(sid));
+                        cnt++;
+                        if (cnt >= TF_MAXHITS) { overflow = true; sp = 0; }   // full chunk: the fallback kernel takes this ray
+                    }
+                }
+            }
+            if (sp == 0) { node = STACK_EMPTY; break; }
+            sp--;
+            node = (sp < TF_STACK) ? sstack[sp * TF_THREADS] : lstack[sp - TF_STACK];
+        }
     }
 }
 
@@ -221,6 +235,23 @@ __device__ __forceinline__ float half_transpose_reduce(float (&v)[16], int h) {
         }
     }
     return v[0];
+}
+
+// ascending bitonic sort of (t, id) across the 16 lanes of a half-warp; empty slots carry t = +inf
+__device__ __forceinline__ void half_bitonic_sort(float& t, int& id, int h) {
+#pragma unroll
+    for (int k = 2; k <= 16; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const float ot = __shfl_xor_sync(0xffffffffu, t, j, 16);
+            const int oi = __shfl_xor_sync(0xffffffffu, id, j, 16);
+            const bool asc = (h & k) == 0;
+            const bool lower = (h & j) == 0;
+            const bool mine_first = (t < ot) || (t == ot && id < oi);
+            const bool keep_mine = (lower == asc) ? mine_first : !mine_first;
+            if (!keep_mine) { t = ot; id = oi; }
+        }
+    }
 }
 
 struct HitEval {
@@ -341,10 +372,12 @@ __global__ void __launch_bounds__(256) shade_fwd_kernel(const FastParams p, int 
     float basis[16];
     if (use_sh) sh_basis(a.sh_degree, normalize3(ray_d), basis);
     const bool valid = live && h < cnt;
-    float2 hit = make_float2(0.0f, 0.0f);
-    if (valid) hit = p.hits[ray * TF_MAXHITS + h];
+    float hit_t = TR_DEPTH_INF * 4.0f;
+    int hit_id = 0x7fffffff;
+    if (valid) { const float2 hit = p.hits[ray * TF_MAXHITS + h]; hit_t = hit.x; hit_id = __float_as_int(hit.y); }
+    half_bitonic_sort(hit_t, hit_id, h);       // slots [0,cnt) now hold the hits in ascending distance
     HitEval e;
-    const float T_final = eval_and_scan(a, valid, hit.x, __float_as_int(hit.y), ray_o, ray_d, basis, nbasis, sh_vec4, campos, h, e);
+    const float T_final = eval_and_scan(a, valid, hit_t, hit_id, ray_o, ray_d, basis, nbasis, sh_vec4, campos, h, e);
 
     // distortion bookkeeping needs exclusive prefix sums of w*m and w*m^2 (forward.cu:405-409)
     const float m = FAR_N / (FAR_N - NEAR_N) * (1.0f - NEAR_N / e.cmd);
@@ -413,10 +446,12 @@ __global__ void __launch_bounds__(256) shade_bwd_kernel(const FastParams p, int 
     const float3 dirn = normalize3(ray_d);
     if (use_sh) sh_basis(a.sh_degree, dirn, basis);
     const bool valid = live && h < cnt;
-    float2 hit = make_float2(0.0f, 0.0f);
-    if (valid) hit = p.hits[ray * TF_MAXHITS + h];
+    float hit_t = TR_DEPTH_INF * 4.0f;
+    int hit_id = 0x7fffffff;
+    if (valid) { const float2 hit = p.hits[ray * TF_MAXHITS + h]; hit_t = hit.x; hit_id = __float_as_int(hit.y); }
+    half_bitonic_sort(hit_t, hit_id, h);
     HitEval e;
-    eval_and_scan(a, valid, hit.x, __float_as_int(hit.y), ray_o, ray_d, basis, nbasis, sh_vec4, campos, h, e);
+    eval_and_scan(a, valid, hit_t, hit_id, ray_o, ray_d, basis, nbasis, sh_vec4, campos, h, e);
 
     // inclusive prefix sums the reference keeps in C, O, D, N while walking front to back
     const float Cx = seg_scan_add(e.w * e.c.x, h), Cy = seg_scan_add(e.w * e.c.y, h), Cz = seg_scan_add(e.w * e.c.z, h);
@@ -542,6 +577,10 @@ int trace_forward_fast(Lbvh& bvh, unsigned int* counter, unsigned long long* sta
     carve_cache((char*)cache, a.H, a.W, p);
     p.work_counter = counter;
     p.stats = stats;
+    {
+        const char* e = getenv("ENVGS_TRACE_REFILL");
+        p.refill_threshold = e ? atoi(e) : 20;
+    }
     if (a.H >= 4) { p.tiles_x = (a.W + 7) / 8; p.n_items = p.tiles_x * ((a.H + 3) / 4); }
     else { p.tiles_x = 0; p.n_items = (int)(((long long)a.H * a.W + 31) / 32); }
     const int R = a.H * a.W;
