@@ -52,8 +52,9 @@ int trace_forward_impl(Lbvh& bvh, unsigned int* counter, unsigned long long* sta
 int trace_backward_impl(Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_grads& g, cudaStream_t stream);
 size_t trace_cache_bytes(int H, int W);
 bool trace_fast_eligible(const envgs_trace_args& a, const void* cache);
-int trace_forward_fast(Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_out& o, void* cache, cudaStream_t stream);
-int trace_backward_fast(Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_grads& g, void* cache, cudaStream_t stream);
+struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; };
+int trace_forward_fast(Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_out& o, void* cache, cudaStream_t stream, const SideStream& side);
+int trace_backward_fast(Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_grads& g, void* cache, cudaStream_t stream, const SideStream& side);
 
 }  // namespace envgs
 
@@ -61,6 +62,7 @@ struct envgs_tracer {
     envgs::Lbvh bvh;
     unsigned int* counter = nullptr;       // [0]: persistent-warp work counter; stats live 64 bytes further
     bool stats_on = false;
+    envgs::SideStream side{nullptr, nullptr, nullptr};
     unsigned long long* stats() { return stats_on ? reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(counter) + 64) : nullptr; }
 };
 
@@ -171,6 +173,14 @@ envgs_tracer* envgs_tracer_create(void) {
         delete h;
         return nullptr;
     }
+    if (cudaStreamCreateWithFlags(&h->side.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->side.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->side.join, cudaEventDisableTiming) != cudaSuccess) {
+        set_error("could not create the tracer's side stream: %s", cudaGetErrorString(cudaGetLastError()));
+        cudaFree(h->counter);
+        delete h;
+        return nullptr;
+    }
     return h;
 }
 
@@ -178,6 +188,9 @@ void envgs_tracer_destroy(envgs_tracer* h) {
     if (!h) return;
     if (h->bvh.owns_storage && h->bvh.storage) cudaFree(h->bvh.storage);
     if (h->counter) cudaFree(h->counter);
+    if (h->side.stream) { cudaStreamSynchronize(h->side.stream); cudaStreamDestroy(h->side.stream); }
+    if (h->side.fork) cudaEventDestroy(h->side.fork);
+    if (h->side.join) cudaEventDestroy(h->side.join);
     delete h;
 }
 
@@ -253,7 +266,7 @@ int envgs_trace_forward(envgs_tracer* h, const envgs_trace_args* args, const env
     }
     if (args->training && !out->a_weights) { set_error("a_weights is NULL although training is set"); return ENVGS_ERR_INVALID; }
     if (trace_fast_eligible(*args, out->hit_cache))
-        return trace_forward_fast(h->bvh, h->counter, h->stats(), *args, *out, out->hit_cache, (cudaStream_t)stream);
+        return trace_forward_fast(h->bvh, h->counter, h->stats(), *args, *out, out->hit_cache, (cudaStream_t)stream, h->side);
     return trace_forward_impl(h->bvh, h->counter, h->stats(), *args, *out, (cudaStream_t)stream);
 }
 
@@ -269,7 +282,7 @@ int envgs_trace_backward(envgs_tracer* h, const envgs_trace_args* args, const en
     if (args->shs && !g->dL_dshs) { set_error("dL_dshs is NULL although shs were given"); return ENVGS_ERR_INVALID; }
     if (args->others_precomp && !g->dL_dothers) { set_error("dL_dothers is NULL although others_precomp was given"); return ENVGS_ERR_INVALID; }
     if (trace_fast_eligible(*args, g->hit_cache))
-        return trace_backward_fast(h->bvh, h->counter, h->stats(), *args, *g, g->hit_cache, (cudaStream_t)stream);
+        return trace_backward_fast(h->bvh, h->counter, h->stats(), *args, *g, g->hit_cache, (cudaStream_t)stream, h->side);
     return trace_backward_impl(h->bvh, h->counter, h->stats(), *args, *g, (cudaStream_t)stream);
 }
 

@@ -25,6 +25,7 @@ void lbvh_carve(Lbvh& t, char* base, int P) {
     char* p = base;
     size_t n = (size_t)(P > 0 ? P : 1);
     carve_one(p, t.nodes, n);
+    carve_one(p, t.nodes4, n);
     carve_one(p, t.prims, n);
     carve_one(p, t.leaf_lo, 4 * n);
     carve_one(p, t.leaf_hi, 4 * n);
@@ -233,6 +234,40 @@ __global__ void single_prim_kernel(const float4* __restrict__ leaf_lo, const flo
     nodes[0].child1 = ~0;
 }
 
+// Collapse the binary tree to 4-wide nodes: node i adopts its grandchildren (a leaf child is adopted as is).
+__global__ void __launch_bounds__(256) collapse4_kernel(int n_internal, const BvhNode* __restrict__ nodes, Bvh4Node* __restrict__ nodes4) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_internal) return;
+    const float* nf = reinterpret_cast<const float*>(&nodes[i]);
+    const int c[2] = {nodes[i].child0, nodes[i].child1};
+    Bvh4Node out;
+    int k = 0;
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        if (c[s] < 0) {
+            const float* b = nf + 6 * s;
+            out.s[k].a = make_float4(b[0], b[1], b[2], b[3]);
+            out.s[k].b = make_float4(b[4], b[5], __int_as_float(c[s]), 0.0f);
+            k++;
+        } else {
+            const float* cf = reinterpret_cast<const float*>(&nodes[c[s]]);
+            const int g[2] = {nodes[c[s]].child0, nodes[c[s]].child1};
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const float* b = cf + 6 * q;
+                out.s[k].a = make_float4(b[0], b[1], b[2], b[3]);
+                out.s[k].b = make_float4(b[4], b[5], __int_as_float(g[q]), 0.0f);
+                k++;
+            }
+        }
+    }
+    for (; k < 4; k++) {
+        out.s[k].a = make_float4(FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX);
+        out.s[k].b = make_float4(-FLT_MAX, -FLT_MAX, __int_as_float(~0), 0.0f);
+    }
+    nodes4[i] = out;
+}
+
 int lbvh_build(Lbvh& t, const float* vertices, int P, bool rebuild, cudaStream_t stream) {
     if (P <= 0) { t.P = 0; return ENVGS_OK; }
     ENVGS_TIMED("bvh_build", stream);
@@ -246,6 +281,8 @@ int lbvh_build(Lbvh& t, const float* vertices, int P, bool rebuild, cudaStream_t
     if (P == 1) {
         single_prim_kernel<<<1, 1, 0, stream>>>((const float4*)t.leaf_lo, (const float4*)t.leaf_hi, t.nodes);
         ENVGS_LAUNCH_CHECK("bvh_single", false, stream);
+        collapse4_kernel<<<1, 32, 0, stream>>>(1, t.nodes, t.nodes4);
+        ENVGS_LAUNCH_CHECK("bvh_collapse4", false, stream);
         t.P = 1;
         return ENVGS_OK;
     }
@@ -262,6 +299,8 @@ int lbvh_build(Lbvh& t, const float* vertices, int P, bool rebuild, cudaStream_t
     refit_kernel<<<blocks, 256, 0, stream>>>(P, t.vals_sorted, (const float4*)t.leaf_lo, (const float4*)t.leaf_hi, t.nodes,
                                              t.parent, t.flags);
     ENVGS_LAUNCH_CHECK("bvh_refit", false, stream);
+    collapse4_kernel<<<(P - 1 + 255) / 256, 256, 0, stream>>>(P - 1, t.nodes, t.nodes4);
+    ENVGS_LAUNCH_CHECK("bvh_collapse4", false, stream);
     t.P = P;
     return ENVGS_OK;
 }

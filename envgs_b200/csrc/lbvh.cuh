@@ -25,6 +25,16 @@ struct __align__(16) QuadPrim {
 };
 static_assert(sizeof(QuadPrim) == 64, "QuadPrim must be 64 bytes");
 
+// 4-wide node for the fast traversal kernel: slot j (32 B) = {lo.xyz, hi.x | hi.yz, child link, pad}, so the four lanes
+// that cooperate on one ray read one 128-byte line with two LDG.128 each (slot j at byte offset 32*j).
+// Child link: >= 0 internal node (same index space as BvhNode), < 0 ~surfel; empty slots have an inverted box.
+struct __align__(16) Bvh4Slot {
+    float4 a;   // lo.xyz, hi.x
+    float4 b;   // hi.y, hi.z, link (int bits), 0
+};
+struct __align__(128) Bvh4Node { Bvh4Slot s[4]; };
+static_assert(sizeof(Bvh4Node) == 128, "Bvh4Node must be 128 bytes");
+
 struct Lbvh {
     int P = 0;              // surfels in the current tree
     int capacity = 0;       // surfels the storage can hold
@@ -33,6 +43,7 @@ struct Lbvh {
     bool owns_storage = false;
     // carved views
     BvhNode* nodes = nullptr;
+    Bvh4Node* nodes4 = nullptr;     // collapsed 4-wide view (one per binary node; only even-depth ones are reachable)
     QuadPrim* prims = nullptr;
     float* leaf_lo = nullptr;      // 3*P (xyz interleaved as float4? no: 4 floats per leaf -> lo.xyz,_ )
     float* leaf_hi = nullptr;

@@ -20,11 +20,14 @@ namespace envgs {
 constexpr int TF_THREADS = 128;
 constexpr int TF_STACK = 32;
 constexpr int TF_LSTACK = 64;
+constexpr int T4_STACK = 48;                // per-ray traversal stack (shared by the ray's 4 lanes)
+constexpr int T4_LEAFQ = 32;                // queued leaves per ray between two quad-test phases
 constexpr int TF_MAXHITS = 16;               // list capacity; a usable list has at most 15 entries
 constexpr int STACK_EMPTY = (int)0x80000000;
 
 struct FastParams {
     const BvhNode* nodes;
+    const Bvh4Node* nodes4;
     const QuadPrim* prims;
     envgs_trace_args a;
     envgs_trace_out o;
@@ -73,133 +76,156 @@ __device__ __forceinline__ bool ray_of_index(const FastParams& p, unsigned int k
     return row < H && col < W;
 }
 
+// FOUR lanes per ray on a 4-wide BVH.  With one ray per lane every node visit is 32 scattered 16-byte loads per
+// instruction = 32 L1 wavefronts, and the kernel was bound by the L1 wavefront rate (ncu: L1 hit 49 %, issue 59 %).
+// Here lane j of a group loads child slot j (32 B) of the 128-byte node, so a visit costs the group ONE cache line
+// (two wavefronts for 8 rays per instruction), each lane slab-tests one child, and the hit masks are combined with a
+// group-wide ballot.  Reached leaves are queued and quad-tested four at a time (one per lane).
 __global__ void __launch_bounds__(TF_THREADS) traverse_kernel(const FastParams p) {
-    __shared__ int s_stack[TF_STACK * TF_THREADS];
+    __shared__ int s_stack[(TF_THREADS / 4) * T4_STACK];
+    __shared__ int s_leafq[(TF_THREADS / 4) * T4_LEAFQ];
     const int lane = threadIdx.x & 31;
-    int* sstack = s_stack + threadIdx.x;
+    const int sub = lane & 3;
+    const int gshift = lane & ~3;
+    const unsigned int lower = (1u << sub) - 1u;
+    int* gstack = s_stack + (threadIdx.x >> 2) * T4_STACK;
+    int* gleaf = s_leafq + (threadIdx.x >> 2) * T4_LEAFQ;
     const int W = p.a.W;
-    const BvhNode* __restrict__ nodes = p.nodes;
+    const Bvh4Node* __restrict__ nodes4 = p.nodes4;
     const QuadPrim* __restrict__ prims = p.prims;
-    const unsigned int total = (unsigned int)p.n_items * 32u;   // ray slots (tiles are padded to 32)
+    const unsigned int total = (unsigned int)p.n_items * 32u;
 
-    int node = STACK_EMPTY;        // STACK_EMPTY <=> this lane has no ray in flight
-    bool have_ray = false, exhausted = false;
+    // per-ray state, replicated in the four lanes of the group
+    int node = STACK_EMPTY;
+    bool have_ray = false, exhausted = false, overflow = false;
     size_t ray = 0;
     float3 o = f3(0, 0, 0), d = f3(0, 0, 1), inv = f3(0, 0, 0);
-    int cnt = 0, sp = 0;
-    bool overflow = false;
+    int cnt = 0, sp = 0, nleaf = 0;
     unsigned int st_nodes = 0, st_prims = 0;
-    int lstack[TF_LSTACK];
 
     while (true) {
-        // ---- retire finished rays, refill idle lanes ----
-        const bool idle = (node == STACK_EMPTY);
+        // ---- retire finished rays, refill idle groups (all 32 lanes are converged here) ----
+        const bool idle = (node == STACK_EMPTY) && nleaf == 0;
         if (idle && have_ray) {
-            if (overflow) {
-                p.counts[ray] = -1;
-                const unsigned int k = atomicAdd(p.overflow_count, 1u);
-                p.overflow_list[k] = (int)ray;
-            } else {
-                p.counts[ray] = cnt;
-            }
-            if (p.stats) {
-                atomicAdd(&p.stats[0], 1ull); atomicAdd(&p.stats[1], (unsigned long long)st_nodes);
-                atomicAdd(&p.stats[2], (unsigned long long)st_prims); atomicAdd(&p.stats[3], (unsigned long long)cnt);
-                atomicAdd(&p.stats[4], 1ull);
+            if (sub == 0) {
+                if (overflow) {
+                    p.counts[ray] = -1;
+                    const unsigned int k = atomicAdd(p.overflow_count, 1u);
+                    p.overflow_list[k] = (int)ray;
+                } else {
+                    p.counts[ray] = cnt;
+                }
+                if (p.stats) {
+                    atomicAdd(&p.stats[0], 1ull); atomicAdd(&p.stats[1], (unsigned long long)st_nodes);
+                    atomicAdd(&p.stats[2], (unsigned long long)st_prims); atomicAdd(&p.stats[3], (unsigned long long)cnt);
+                    atomicAdd(&p.stats[4], 1ull);
+                }
             }
             have_ray = false;
         }
-        const unsigned int want = __ballot_sync(0xffffffffu, idle && !exhausted);
+        const bool gwant = idle && !exhausted;
+        const unsigned int want = __ballot_sync(0xffffffffu, gwant && sub == 0);
         if (want) {
             const int leader = __ffs(want) - 1;
             unsigned int base = 0;
             if (lane == leader) base = atomicAdd(p.work_counter, (unsigned int)__popc(want));
             base = __shfl_sync(0xffffffffu, base, leader);
-            if (idle && !exhausted) {
-                unsigned int k = base + __popc(want & ((1u << lane) - 1u));
-                // skip padding slots (pixels outside the image in the last tile column/row)
+            if (gwant) {
+                const unsigned int k = base + __popc(want & ((1u << gshift) - 1u));
                 int row = 0, col = 0;
                 bool ok = false;
-                if (k < total) ok = ray_of_index(p, k, row, col);
+                if (k < total) ok = ray_of_index(p, k, row, col);   // padding slots of edge tiles are skipped
                 else exhausted = true;
                 if (ok) {
                     ray = (size_t)row * W + col;
                     o = ld3(p.a.ray_o, (int)ray); d = ld3(p.a.ray_d, (int)ray);
                     inv = f3(safe_inv_f(d.x), safe_inv_f(d.y), safe_inv_f(d.z));
-                    cnt = 0; sp = 0; overflow = false; st_nodes = 0; st_prims = 0;
+                    cnt = 0; sp = 0; nleaf = 0; overflow = false; st_nodes = 0; st_prims = 0;
                     have_ray = true;
                     node = isfinite(d.x + d.y + d.z + o.x + o.y + o.z) ? 0 : STACK_EMPTY;
                 }
             }
         }
-        if (__all_sync(0xffffffffu, exhausted && node == STACK_EMPTY && !have_ray)) break;
+        if (__all_sync(0xffffffffu, exhausted && !have_ray)) break;
 
-        // ---- internal nodes ----
-        while (node >= 0) {
-            const float4 A = __ldg(&nodes[node].a), B = __ldg(&nodes[node].b), C = __ldg(&nodes[node].c);
-            const int c0 = __ldg(&nodes[node].child0), c1 = __ldg(&nodes[node].child1);
-            st_nodes++;
-            bool h0, h1;
-            {
-                float ax = (A.x - o.x) * inv.x, bx = (A.w - o.x) * inv.x;
-                float ay = (A.y - o.y) * inv.y, by = (B.x - o.y) * inv.y;
-                float az = (A.z - o.z) * inv.z, bz = (B.y - o.z) * inv.z;
-                float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
-                float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) * 1.0000004f;
-                h0 = (tn <= tf) && (tf > 0.0f);
+        // ---- phase 1: 4-wide internal nodes; hit leaves are queued, hit internal children pushed ----
+        // The warp stays converged (full-mask votes, idle groups predicated off): per-group vote masks would split the
+        // warp into eight 4-lane fragments that are issued one after the other.
+        const bool can_refill = __any_sync(0xffffffffu, idle && !exhausted);
+        while (true) {
+            const bool act = node != STACK_EMPTY && nleaf <= T4_LEAFQ - 4 && sp <= T4_STACK - 4;
+            const unsigned int am = __ballot_sync(0xffffffffu, act);
+            if (am == 0u) break;
+            if (can_refill && __popc(am) < p.refill_threshold) break;   // let idle groups fetch new rays (Aila & Laine 2009)
+            bool hit_leaf = false, hit_int = false;
+            int link = 0;
+            if (act) {
+                const Bvh4Slot* __restrict__ sl = &nodes4[node].s[sub];
+                const float4 A = __ldg(&sl->a), B = __ldg(&sl->b);
+                link = __float_as_int(B.z);
+                st_nodes++;
+                const float ax = (A.x - o.x) * inv.x, bx = (A.w - o.x) * inv.x;
+                const float ay = (A.y - o.y) * inv.y, by = (B.x - o.y) * inv.y;
+                const float az = (A.z - o.z) * inv.z, bz = (B.y - o.z) * inv.z;
+                const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+                const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) * 1.0000004f;
+                const bool hit = (tn <= tf) && (tf > 0.0f);
+                hit_leaf = hit && link < 0;
+                hit_int = hit && link >= 0;
             }
-            {
-                float ax = (B.z - o.x) * inv.x, bx = (C.y - o.x) * inv.x;
-                float ay = (B.w - o.y) * inv.y, by = (C.z - o.y) * inv.y;
-                float az = (C.x - o.z) * inv.z, bz = (C.w - o.z) * inv.z;
-                float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
-                float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) * 1.0000004f;
-                h1 = (tn <= tf) && (tf > 0.0f);
+            const unsigned int m_leaf = (__ballot_sync(0xffffffffu, hit_leaf) >> gshift) & 0xFu;
+            const unsigned int m_int = (__ballot_sync(0xffffffffu, hit_int) >> gshift) & 0xFu;
+            if (hit_leaf) gleaf[nleaf + __popc(m_leaf & lower)] = ~link;
+            if (hit_int) gstack[sp + __popc(m_int & lower)] = link;
+            __syncwarp();
+            if (act) {
+                nleaf += __popc(m_leaf);
+                sp += __popc(m_int);
+                if (sp == 0) node = STACK_EMPTY;
+                else { sp--; node = gstack[sp]; }
             }
-            if (h0 && h1) {
-                if (sp < TF_STACK) sstack[sp * TF_THREADS] = c1;
-                else if (sp < TF_STACK + TF_LSTACK) lstack[sp - TF_STACK] = c1;
-                sp = min(sp + 1, TF_STACK + TF_LSTACK);
-                node = c0;
-            } else if (h0) {
-                node = c0;
-            } else if (h1) {
-                node = c1;
-            } else {
-                if (sp == 0) { node = STACK_EMPTY; break; }
-                sp--;
-                node = (sp < TF_STACK) ? sstack[sp * TF_THREADS] : lstack[sp - TF_STACK];
-            }
-            if (__popc(__activemask()) < p.refill_threshold) break;   // let the idle lanes fetch new rays (Aila & Laine 2009)
+            __syncwarp();
         }
-        // ---- leaves ----
-        while (node < 0 && node != STACK_EMPTY) {
-            const int sid = ~node;
-            st_prims++;
-            const float4 pn = __ldg(&prims[sid].n);
-            const float4 pv = __ldg(&prims[sid].v1);
-            const float3 n = f3(pn.x, pn.y, pn.z);
-            const float q = dot(n, d);
-            if (q != 0.0f) {
-                const float3 v1 = f3(pv.x, pv.y, pv.z);
-                const float t = dot(n, v1 - o) / q;
-                if (t > 0.0f && t < TR_DEPTH_INF) {
-                    const float4 pu = __ldg(&prims[sid].eu);
-                    const float4 pw = __ldg(&prims[sid].ev);
-                    const float3 r = (o + t * d) - v1;
-                    const float a = dot(r, f3(pu.x, pu.y, pu.z)) * pv.w;
-                    const float b = dot(r, f3(pw.x, pw.y, pw.z)) * pu.w;
-                    if (pw.w != 0.0f && a >= 0.0f && a <= 1.0f && b >= 0.0f && b <= 1.0f) {
-                        if (cnt < TF_MAXHITS) p.hits[ray * TF_MAXHITS + cnt] = make_float2(t, __int_as_float(sid));
-                        cnt++;
-                        if (cnt >= TF_MAXHITS) { overflow = true; sp = 0; }   // full chunk: the fallback kernel takes this ray
+        if (sp > T4_STACK - 4 && node != STACK_EMPTY && nleaf <= T4_LEAFQ - 4) {
+            // stack capacity reached (pathologically deep tree): hand the ray to the general kernel
+            overflow = true; node = STACK_EMPTY; sp = 0; nleaf = 0;
+        }
+        // ---- phase 2: queued quads, four at a time (warp-uniform trip count) ----
+        for (int i0 = 0; __any_sync(0xffffffffu, i0 < nleaf); i0 += 4) {
+            const int i = i0 + sub;
+            bool hit = false;
+            float t = 0.0f;
+            int sid = 0;
+            if (i < nleaf) {
+                sid = gleaf[i];
+                st_prims++;
+                const float4 pn = __ldg(&prims[sid].n);
+                const float4 pv = __ldg(&prims[sid].v1);
+                const float3 n = f3(pn.x, pn.y, pn.z);
+                const float q = dot(n, d);
+                if (q != 0.0f) {
+                    const float3 v1 = f3(pv.x, pv.y, pv.z);
+                    t = dot(n, v1 - o) / q;
+                    if (t > 0.0f && t < TR_DEPTH_INF) {
+                        const float4 pu = __ldg(&prims[sid].eu);
+                        const float4 pw = __ldg(&prims[sid].ev);
+                        const float3 r = (o + t * d) - v1;
+                        const float a = dot(r, f3(pu.x, pu.y, pu.z)) * pv.w;
+                        const float b = dot(r, f3(pw.x, pw.y, pw.z)) * pu.w;
+                        hit = pw.w != 0.0f && a >= 0.0f && a <= 1.0f && b >= 0.0f && b <= 1.0f;
                     }
                 }
             }
-            if (sp == 0) { node = STACK_EMPTY; break; }
-            sp--;
-            node = (sp < TF_STACK) ? sstack[sp * TF_THREADS] : lstack[sp - TF_STACK];
+            const unsigned int hm = (__ballot_sync(0xffffffffu, hit) >> gshift) & 0xFu;
+            if (hit) {
+                const int slot = cnt + __popc(hm & lower);
+                if (slot < TF_MAXHITS) p.hits[ray * TF_MAXHITS + slot] = make_float2(t, __int_as_float(sid));
+            }
+            cnt += __popc(hm);
+            if (cnt >= TF_MAXHITS && !overflow) { overflow = true; sp = 0; node = STACK_EMPTY; nleaf = 0; }   // full chunk: general kernel
         }
+        nleaf = 0;
+        __syncwarp();
     }
 }
 
@@ -413,7 +439,13 @@ __global__ void __launch_bounds__(256) shade_fwd_kernel(const FastParams p, int 
     }
 }
 
+constexpr int GR_STRIDE = 20;   // floats per staged hit-gradient record
+
 __global__ void __launch_bounds__(256) shade_bwd_kernel(const FastParams p, int R) {
+    // per-hit gradient records staged in shared memory so the 61 atomics of a contributing hit are issued by the whole
+    // half-warp (15 small components in one instruction, 48 SH components in three) instead of one lane after another
+    __shared__ float s_rec[SH_RAYS_PER_BLOCK * 16 * GR_STRIDE];
+    __shared__ float s_basis[SH_RAYS_PER_BLOCK * 16];
     const envgs_trace_args& a = p.a;
     const envgs_trace_grads& g = p.g;
     const int h = threadIdx.x & 15;
@@ -472,10 +504,11 @@ __global__ void __launch_bounds__(256) shade_bwd_kernel(const FastParams p, int 
             dL_dalpha += dL_drgb[ch] * (T_prev * cc[ch] - (seg_rgb[ch] - Cc[ch]) / (1.0f - alpha));
             dL_dalpha += dL_drgb[ch] * a.background[ch] * (-T_final_saved / (1.0f - alpha));
         }
+        float dL_doth[2] = {0.0f, 0.0f};
         if (a.others_precomp != nullptr) {
 #pragma unroll
             for (int ch = 0; ch < 2; ch++) {
-                atomicAdd(&g.dL_dothers[2 * (size_t)gidx + ch], dL_daux[ch] * w);
+                dL_doth[ch] = dL_daux[ch] * w;
                 dL_dalpha += dL_daux[ch] * (T_prev * e.oth[ch] - (seg_aux[ch] - O[ch]) / (1.0f - alpha));
             }
         }
@@ -484,7 +517,7 @@ __global__ void __launch_bounds__(256) shade_bwd_kernel(const FastParams p, int 
         const float3 dL_dN = dL_dnorm * w;
         dL_dalpha += sum3(dL_dnorm * (T_prev * e.normal - (seg_norm - f3(Nx, Ny, Nz)) / (1.0f - alpha)));
         const float dL_dG = dL_dalpha * e.opac;
-        atomicAdd(&g.dL_dopacities[gidx], dL_dalpha * G);
+        const float dL_dopac = dL_dalpha * G;   // straight-through cap (backward.cu:801-806)
 
         // compute_transmat_uv_backward (backward.cu:233-335), plane form t = m.(mu-o)/(m.d), m = t_u x t_v
         const float2 dL_duv = make_float2(dL_dG * -G * e.uv.x, dL_dG * -G * e.uv.y);
@@ -509,28 +542,63 @@ __global__ void __launch_bounds__(256) shade_bwd_kernel(const FastParams p, int 
         Rot3 gR; gR.c0 = dR0; gR.c1 = dR1; gR.c2 = dR2;
         const float4 dL_drot = quat_to_rot_vjp(e.rot, gR);
 
-        atomicAdd(&g.dL_dscales[2 * (size_t)gidx + 0], dL_dscale.x);
-        atomicAdd(&g.dL_dscales[2 * (size_t)gidx + 1], dL_dscale.y);
-        atomicAdd(&g.dL_drotations[4 * (size_t)gidx + 0], dL_drot.x);
-        atomicAdd(&g.dL_drotations[4 * (size_t)gidx + 1], dL_drot.y);
-        atomicAdd(&g.dL_drotations[4 * (size_t)gidx + 2], dL_drot.z);
-        atomicAdd(&g.dL_drotations[4 * (size_t)gidx + 3], dL_drot.w);
-        atomicAdd(&g.dL_dmeans3D[3 * (size_t)gidx + 0], dL_dmean.x);
-        atomicAdd(&g.dL_dmeans3D[3 * (size_t)gidx + 1], dL_dmean.y);
-        atomicAdd(&g.dL_dmeans3D[3 * (size_t)gidx + 2], dL_dmean.z);
-#pragma unroll
-        for (int ch = 0; ch < 3; ch++) atomicAdd(&g.dL_dcolors[3 * (size_t)gidx + ch], dL_dcolor[ch]);
+        float3 dRGB = f3(0, 0, 0);
         if (use_sh) {
-            const float3 dRGB = f3(e.clamped[0] ? 0.0f : dL_dcolor[0], e.clamped[1] ? 0.0f : dL_dcolor[1], e.clamped[2] ? 0.0f : dL_dcolor[2]);
-            float* dsh = g.dL_dshs + (size_t)gidx * a.sh_coeffs * 3;
-            for (int k = 0; k < nbasis; k++) {
-                atomicAdd(&dsh[3 * k + 0], basis[k] * dRGB.x);
-                atomicAdd(&dsh[3 * k + 1], basis[k] * dRGB.y);
-                atomicAdd(&dsh[3 * k + 2], basis[k] * dRGB.z);
-            }
+            dRGB = f3(e.clamped[0] ? 0.0f : dL_dcolor[0], e.clamped[1] ? 0.0f : dL_dcolor[1], e.clamped[2] ? 0.0f : dL_dcolor[2]);
             float3 gx, gy, gz;
             sh_dir_grad(a.sh_degree, dirn, a.shs + (size_t)gidx * a.sh_coeffs * 3, gx, gy, gz);
             dL_ddir_sh = f3(dot(gx, dRGB), dot(gy, dRGB), dot(gz, dRGB));
+        }
+        float* rec = s_rec + ((threadIdx.x >> 4) * 16 + h) * GR_STRIDE;
+        rec[0] = dL_dscale.x; rec[1] = dL_dscale.y;
+        rec[2] = dL_drot.x; rec[3] = dL_drot.y; rec[4] = dL_drot.z; rec[5] = dL_drot.w;
+        rec[6] = dL_dmean.x; rec[7] = dL_dmean.y; rec[8] = dL_dmean.z;
+        rec[9] = dL_dcolor[0]; rec[10] = dL_dcolor[1]; rec[11] = dL_dcolor[2];
+        rec[12] = dL_dopac; rec[13] = dL_doth[0]; rec[14] = dL_doth[1];
+        rec[15] = dRGB.x; rec[16] = dRGB.y; rec[17] = dRGB.z;
+        rec[18] = __int_as_float(gidx);
+    }
+    // ---- cooperative scatter: the half-warp walks its contributing hits; lane q owns component q / SH coefficient q ----
+    {
+        float my_basis = 0.0f;
+        if (use_sh) {
+            float* sb = s_basis + (threadIdx.x >> 4) * 16;
+            if (h == 0) {
+#pragma unroll
+                for (int k = 0; k < 16; k++) sb[k] = k < nbasis ? basis[k] : 0.0f;
+            }
+            __syncwarp();
+            my_basis = sb[h];
+        } else {
+            __syncwarp();
+        }
+        const unsigned int half_shift = (threadIdx.x & 16);
+        unsigned int cm = (__ballot_sync(0xffffffffu, e.contrib) >> half_shift) & 0xffffu;
+        const bool has_oth = a.others_precomp != nullptr;
+        while (__any_sync(0xffffffffu, cm != 0u)) {
+            if (cm != 0u) {
+                const int hit = __ffs(cm) - 1;
+                cm &= cm - 1u;
+                const float* rec = s_rec + ((threadIdx.x >> 4) * 16 + hit) * GR_STRIDE;
+                const size_t gi = (size_t)__float_as_int(rec[18]);
+                if (h < 15) {
+                    const float v = rec[h];
+                    float* dst;
+                    if (h < 2) dst = g.dL_dscales + 2 * gi + h;
+                    else if (h < 6) dst = g.dL_drotations + 4 * gi + (h - 2);
+                    else if (h < 9) dst = g.dL_dmeans3D + 3 * gi + (h - 6);
+                    else if (h < 12) dst = g.dL_dcolors + 3 * gi + (h - 9);
+                    else if (h == 12) dst = g.dL_dopacities + gi;
+                    else dst = has_oth ? g.dL_dothers + 2 * gi + (h - 13) : nullptr;
+                    if (dst != nullptr) atomicAdd(dst, v);
+                }
+                if (use_sh && h < nbasis) {
+                    float* dsh = g.dL_dshs + gi * a.sh_coeffs * 3 + 3 * h;
+                    atomicAdd(dsh + 0, my_basis * rec[15]);
+                    atomicAdd(dsh + 1, my_basis * rec[16]);
+                    atomicAdd(dsh + 2, my_basis * rec[17]);
+                }
+            }
         }
     }
     // per-ray gradients: sum over the 16 hits
@@ -561,8 +629,12 @@ bool trace_fast_eligible(const envgs_trace_args& a, const void* cache) {
     return !(f && f[0] == '1');
 }
 
+// The few rays with a full first chunk run in the general kernel on a side stream, concurrently with the shading kernel
+// (they write disjoint rays); the caller's stream joins before returning control.
+struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; };
+
 int trace_forward_fast(Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_out& o,
-                       void* cache, cudaStream_t stream) {
+                       void* cache, cudaStream_t stream, const SideStream& side) {
     static int sm_count = 0, occ = 0;
     if (sm_count == 0) {
         int dev = 0;
@@ -573,13 +645,13 @@ int trace_forward_fast(Lbvh& bvh, unsigned int* counter, unsigned long long* sta
     }
     FastParams p;
     memset(&p, 0, sizeof(p));
-    p.nodes = bvh.nodes; p.prims = bvh.prims; p.a = a; p.o = o;
+    p.nodes = bvh.nodes; p.nodes4 = bvh.nodes4; p.prims = bvh.prims; p.a = a; p.o = o;
     carve_cache((char*)cache, a.H, a.W, p);
     p.work_counter = counter;
     p.stats = stats;
     {
         const char* e = getenv("ENVGS_TRACE_REFILL");
-        p.refill_threshold = e ? atoi(e) : 20;
+        p.refill_threshold = e ? atoi(e) : 28;
     }
     if (a.H >= 4) { p.tiles_x = (a.W + 7) / 8; p.n_items = p.tiles_x * ((a.H + 3) / 4); }
     else { p.tiles_x = 0; p.n_items = (int)(((long long)a.H * a.W + 31) / 32); }
@@ -587,35 +659,47 @@ int trace_forward_fast(Lbvh& bvh, unsigned int* counter, unsigned long long* sta
     ENVGS_CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream));
     ENVGS_CUDA_TRY(cudaMemsetAsync(p.overflow_count, 0, sizeof(unsigned int), stream));
     int blocks = sm_count * occ;
-    int need = (p.n_items + (TF_THREADS / 32) - 1) / (TF_THREADS / 32);
+    int need = (p.n_items * 32 + (TF_THREADS / 4) - 1) / (TF_THREADS / 4);
     if (blocks > need) blocks = need > 0 ? need : 1;
     {
         ENVGS_TIMED("trace_traverse", stream);
         traverse_kernel<<<blocks, TF_THREADS, 0, stream>>>(p);
         ENVGS_LAUNCH_CHECK("trace_traverse", false, stream);
     }
+    // rays whose first chunk was full: the reference's multi-chunk loop, run by the general kernel on the device-side list
+    ENVGS_CUDA_TRY(cudaEventRecord(side.fork, stream));
+    ENVGS_CUDA_TRY(cudaStreamWaitEvent(side.stream, side.fork, 0));
+    int rc = launch_trace(false, bvh, counter, stats, a, &o, nullptr, p.overflow_list, p.overflow_count, side.stream);
+    if (rc != ENVGS_OK) return rc;
+    ENVGS_CUDA_TRY(cudaEventRecord(side.join, side.stream));
     {
         ENVGS_TIMED("trace_shade_fwd", stream);
         shade_fwd_kernel<<<(R + SH_RAYS_PER_BLOCK - 1) / SH_RAYS_PER_BLOCK, 256, 0, stream>>>(p, R);
         ENVGS_LAUNCH_CHECK("trace_shade_fwd", false, stream);
     }
-    // rays whose first chunk was full: the reference's multi-chunk loop, run by the monolithic kernel on the device-side list
-    return launch_trace(false, bvh, counter, stats, a, &o, nullptr, p.overflow_list, p.overflow_count, stream);
+    ENVGS_CUDA_TRY(cudaStreamWaitEvent(stream, side.join, 0));
+    return ENVGS_OK;
 }
 
 int trace_backward_fast(Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_grads& g,
-                        void* cache, cudaStream_t stream) {
+                        void* cache, cudaStream_t stream, const SideStream& side) {
     FastParams p;
     memset(&p, 0, sizeof(p));
     p.nodes = bvh.nodes; p.prims = bvh.prims; p.a = a; p.g = g;
     carve_cache((char*)cache, a.H, a.W, p);
     const int R = a.H * a.W;
+    ENVGS_CUDA_TRY(cudaEventRecord(side.fork, stream));
+    ENVGS_CUDA_TRY(cudaStreamWaitEvent(side.stream, side.fork, 0));
+    int rc = launch_trace(true, bvh, counter, stats, a, nullptr, &g, p.overflow_list, p.overflow_count, side.stream);
+    if (rc != ENVGS_OK) return rc;
+    ENVGS_CUDA_TRY(cudaEventRecord(side.join, side.stream));
     {
         ENVGS_TIMED("trace_shade_bwd", stream);
         shade_bwd_kernel<<<(R + SH_RAYS_PER_BLOCK - 1) / SH_RAYS_PER_BLOCK, 256, 0, stream>>>(p, R);
         ENVGS_LAUNCH_CHECK("trace_shade_bwd", false, stream);
     }
-    return launch_trace(true, bvh, counter, stats, a, nullptr, &g, p.overflow_list, p.overflow_count, stream);
+    ENVGS_CUDA_TRY(cudaStreamWaitEvent(stream, side.join, 0));
+    return ENVGS_OK;
 }
 
 }  // namespace envgs
