@@ -88,8 +88,9 @@ __global__ void __launch_bounds__(256) prim_kernel(int P, const float* __restric
                     fmaxf(fmaxf(v0.z, v1.z), fmaxf(v2.z, v3.z)));
             // pad so flat quads keep a non-zero slab and rounding in the plane test cannot escape the box
             float3 ext = hi - lo;
-            float pad = 1e-5f * fmaxf(fmaxf(ext.x, ext.y), ext.z) +
-                        4e-7f * fmaxf(fmaxf(fmaxf(fabsf(lo.x), fabsf(hi.x)), fmaxf(fabsf(lo.y), fabsf(hi.y))),
+            // (slab-test rounding is ~2.4e-7 * |coordinate| per plane; keep an order of magnitude of head-room)
+            float pad = 1e-4f * fmaxf(fmaxf(ext.x, ext.y), ext.z) +
+                        4e-6f * fmaxf(fmaxf(fmaxf(fabsf(lo.x), fabsf(hi.x)), fmaxf(fabsf(lo.y), fabsf(hi.y))),
                                       fmaxf(fabsf(lo.z), fabsf(hi.z)));
             lo = lo - f3(pad, pad, pad);
             hi = hi + f3(pad, pad, pad);

@@ -40,6 +40,7 @@ struct FastParams {
     unsigned long long* stats;
     int n_items, tiles_x;
     int refill_threshold;         // leave an inner traversal loop when fewer lanes than this are still in it
+    int debug_flags;              // development only: 1 = skip SH atomics, 2 = skip small atomics (timing experiments)
 };
 
 size_t trace_cache_bytes(int H, int W) {
@@ -294,9 +295,11 @@ struct HitEval {
 };
 
 // Evaluate this lane's hit and run the transmittance scan.  Returns T_final (same for the 16 lanes).
+// When `dL_drgb` is given (backward), shU[k] = w * sum_c sh[k][c] * dL/drgb_c (unclamped channels): the per-hit part of
+// dL/d(direction) through the SH colour, formed while the coefficients are in registers.
 __device__ __forceinline__ float eval_and_scan(const envgs_trace_args& a, bool valid, float tmx, int gidx, float3 ray_o, float3 ray_d,
                                                const float* __restrict__ basis, int nbasis, bool sh_vec4, float3 campos, int h,
-                                               HitEval& e) {
+                                               HitEval& e, const float* dL_drgb = nullptr, float* shU = nullptr) {
     e.gidx = gidx;
     bool cand = valid;
     e.alpha = 0.0f; e.G = 0.0f; e.cmd = 1.0f; e.opac = 0.0f; e.nsign = 1.0f;
@@ -368,6 +371,24 @@ __device__ __forceinline__ float eval_and_scan(const envgs_trace_args& a, bool v
             res.x += 0.5f; res.y += 0.5f; res.z += 0.5f;
             e.clamped[0] = res.x < 0; e.clamped[1] = res.y < 0; e.clamped[2] = res.z < 0;
             e.c = f3(fmaxf(res.x, 0.0f), fmaxf(res.y, 0.0f), fmaxf(res.z, 0.0f));
+            if (shU != nullptr) {
+                const float gr = e.clamped[0] ? 0.0f : dL_drgb[0] * e.w, gg = e.clamped[1] ? 0.0f : dL_drgb[1] * e.w,
+                            gb = e.clamped[2] ? 0.0f : dL_drgb[2] * e.w;
+                if (sh_vec4) {
+                    const float4* s4 = reinterpret_cast<const float4*>(sh);
+                    float tmp[48];
+#pragma unroll
+                    for (int q = 0; q < 12; q++) {
+                        if (q * 4 < nbasis * 3) { float4 v = __ldg(&s4[q]); tmp[4 * q] = v.x; tmp[4 * q + 1] = v.y; tmp[4 * q + 2] = v.z; tmp[4 * q + 3] = v.w; }
+                        else { tmp[4 * q] = tmp[4 * q + 1] = tmp[4 * q + 2] = tmp[4 * q + 3] = 0.0f; }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 16; k++) shU[k] = k < nbasis ? tmp[3 * k] * gr + tmp[3 * k + 1] * gg + tmp[3 * k + 2] * gb : 0.0f;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 16; k++) shU[k] = k < nbasis ? sh[3 * k] * gr + sh[3 * k + 1] * gg + sh[3 * k + 2] * gb : 0.0f;
+                }
+            }
         } else {
             e.c = ld3(a.colors_precomp, gidx);
         }
@@ -439,6 +460,30 @@ __global__ void __launch_bounds__(256) shade_fwd_kernel(const FastParams p, int 
     }
 }
 
+// d basis_k / d(x,y,z) of the SH polynomials (RAST backward.cu:58-122 collects the same terms per colour channel)
+__device__ __forceinline__ float3 sh_basis_grad(int k, float3 d) {
+    const float x = d.x, y = d.y, z = d.z;
+    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+    switch (k) {
+        case 1: return f3(0.0f, -SH_C1, 0.0f);
+        case 2: return f3(0.0f, 0.0f, SH_C1);
+        case 3: return f3(-SH_C1, 0.0f, 0.0f);
+        case 4: return SH_C2[0] * f3(y, x, 0.0f);
+        case 5: return SH_C2[1] * f3(0.0f, z, y);
+        case 6: return SH_C2[2] * f3(-2.0f * x, -2.0f * y, 4.0f * z);
+        case 7: return SH_C2[3] * f3(z, 0.0f, x);
+        case 8: return SH_C2[4] * f3(2.0f * x, -2.0f * y, 0.0f);
+        case 9: return SH_C3[0] * f3(6.0f * xy, 3.0f * xx - 3.0f * yy, 0.0f);
+        case 10: return SH_C3[1] * f3(yz, xz, xy);
+        case 11: return SH_C3[2] * f3(-2.0f * xy, 4.0f * zz - xx - 3.0f * yy, 8.0f * yz);
+        case 12: return SH_C3[3] * f3(-6.0f * xz, -6.0f * yz, 6.0f * zz - 3.0f * xx - 3.0f * yy);
+        case 13: return SH_C3[4] * f3(4.0f * zz - 3.0f * xx - yy, -2.0f * xy, 8.0f * xz);
+        case 14: return SH_C3[5] * f3(2.0f * xz, -2.0f * yz, xx - yy);
+        case 15: return SH_C3[6] * f3(3.0f * xx - 3.0f * yy, -6.0f * xy, 0.0f);
+        default: return f3(0.0f, 0.0f, 0.0f);
+    }
+}
+
 constexpr int GR_STRIDE = 20;   // floats per staged hit-gradient record
 
 __global__ void __launch_bounds__(256) shade_bwd_kernel(const FastParams p, int R) {
@@ -483,7 +528,10 @@ __global__ void __launch_bounds__(256) shade_bwd_kernel(const FastParams p, int 
     if (valid) { const float2 hit = p.hits[ray * TF_MAXHITS + h]; hit_t = hit.x; hit_id = __float_as_int(hit.y); }
     half_bitonic_sort(hit_t, hit_id, h);
     HitEval e;
-    eval_and_scan(a, valid, hit_t, hit_id, ray_o, ray_d, basis, nbasis, sh_vec4, campos, h, e);
+    float shU[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) shU[k] = 0.0f;
+    eval_and_scan(a, valid, hit_t, hit_id, ray_o, ray_d, basis, nbasis, sh_vec4, campos, h, e, dL_drgb, use_sh ? shU : nullptr);
 
     // inclusive prefix sums the reference keeps in C, O, D, N while walking front to back
     const float Cx = seg_scan_add(e.w * e.c.x, h), Cy = seg_scan_add(e.w * e.c.y, h), Cz = seg_scan_add(e.w * e.c.z, h);
@@ -491,7 +539,7 @@ __global__ void __launch_bounds__(256) shade_bwd_kernel(const FastParams p, int 
     const float Dp = seg_scan_add(e.w * e.cmd, h);
     const float Nx = seg_scan_add(e.w * e.normal.x, h), Ny = seg_scan_add(e.w * e.normal.y, h), Nz = seg_scan_add(e.w * e.normal.z, h);
 
-    float3 g_ray_o = f3(0, 0, 0), g_ray_d = f3(0, 0, 0), dL_ddir_sh = f3(0, 0, 0);
+    float3 g_ray_o = f3(0, 0, 0), g_ray_d = f3(0, 0, 0);
     if (e.contrib) {
         const int gidx = e.gidx;
         const float alpha = e.alpha, T_prev = e.T_prev, w = e.w, G = e.G, cmd = e.cmd;
@@ -545,9 +593,6 @@ __global__ void __launch_bounds__(256) shade_bwd_kernel(const FastParams p, int 
         float3 dRGB = f3(0, 0, 0);
         if (use_sh) {
             dRGB = f3(e.clamped[0] ? 0.0f : dL_dcolor[0], e.clamped[1] ? 0.0f : dL_dcolor[1], e.clamped[2] ? 0.0f : dL_dcolor[2]);
-            float3 gx, gy, gz;
-            sh_dir_grad(a.sh_degree, dirn, a.shs + (size_t)gidx * a.sh_coeffs * 3, gx, gy, gz);
-            dL_ddir_sh = f3(dot(gx, dRGB), dot(gy, dRGB), dot(gz, dRGB));
         }
         float* rec = s_rec + ((threadIdx.x >> 4) * 16 + h) * GR_STRIDE;
         rec[0] = dL_dscale.x; rec[1] = dL_dscale.y;
@@ -590,9 +635,9 @@ __global__ void __launch_bounds__(256) shade_bwd_kernel(const FastParams p, int 
                     else if (h < 12) dst = g.dL_dcolors + 3 * gi + (h - 9);
                     else if (h == 12) dst = g.dL_dopacities + gi;
                     else dst = has_oth ? g.dL_dothers + 2 * gi + (h - 13) : nullptr;
-                    if (dst != nullptr) atomicAdd(dst, v);
+                    if (dst != nullptr && !(p.debug_flags & 2)) atomicAdd(dst, v);
                 }
-                if (use_sh && h < nbasis) {
+                if (use_sh && h < nbasis && !(p.debug_flags & 1)) {
                     float* dsh = g.dL_dshs + gi * a.sh_coeffs * 3 + 3 * h;
                     atomicAdd(dsh + 0, my_basis * rec[15]);
                     atomicAdd(dsh + 1, my_basis * rec[16]);
@@ -604,11 +649,22 @@ __global__ void __launch_bounds__(256) shade_bwd_kernel(const FastParams p, int 
     // per-ray gradients: sum over the 16 hits
     float v[16];
     v[0] = g_ray_o.x; v[1] = g_ray_o.y; v[2] = g_ray_o.z; v[3] = g_ray_d.x; v[4] = g_ray_d.y; v[5] = g_ray_d.z;
-    v[6] = dL_ddir_sh.x; v[7] = dL_ddir_sh.y; v[8] = dL_ddir_sh.z;
 #pragma unroll
-    for (int i = 9; i < 16; i++) v[i] = 0.0f;
+    for (int i = 6; i < 16; i++) v[i] = 0.0f;
     const float tot = half_transpose_reduce(v, h);
-    const float sx = __shfl_sync(0xffffffffu, tot, 6, 16), sy = __shfl_sync(0xffffffffu, tot, 7, 16), sz = __shfl_sync(0xffffffffu, tot, 8, 16);
+    // SH direction gradient: lane k gets U_k = sum over hits of shU[k]; dL/ddir = sum_k U_k * grad basis_k(dir)
+    float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+    if (use_sh) {
+        const float Uk = half_transpose_reduce(shU, h);
+        const float3 gb = sh_basis_grad(h < nbasis ? h : 0, dirn);
+        sx = Uk * gb.x; sy = Uk * gb.y; sz = Uk * gb.z;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            sx += __shfl_xor_sync(0xffffffffu, sx, o, 16);
+            sy += __shfl_xor_sync(0xffffffffu, sy, o, 16);
+            sz += __shfl_xor_sync(0xffffffffu, sz, o, 16);
+        }
+    }
     if (ray_ok && cnt >= 0) {   // overflow rays (cnt < 0) are written by the fallback kernel
         float3 extra = f3(0, 0, 0);
         if (use_sh && live) extra = dnormvdv(ray_d, f3(sx, sy, sz));   // backward.cu:182-184
@@ -687,6 +743,7 @@ int trace_backward_fast(Lbvh& bvh, unsigned int* counter, unsigned long long* st
     memset(&p, 0, sizeof(p));
     p.nodes = bvh.nodes; p.prims = bvh.prims; p.a = a; p.g = g;
     carve_cache((char*)cache, a.H, a.W, p);
+    { const char* e = getenv("ENVGS_DEBUG_FLAGS"); p.debug_flags = e ? atoi(e) : 0; }
     const int R = a.H * a.W;
     ENVGS_CUDA_TRY(cudaEventRecord(side.fork, stream));
     ENVGS_CUDA_TRY(cudaStreamWaitEvent(side.stream, side.fork, 0));

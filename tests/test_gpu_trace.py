@@ -89,8 +89,9 @@ def test_degenerate_rays_and_refit(built_lib):
     tr = SurfelTracer().cuda()
     v, f = scene.quad_vertices(env.means, env.scales, env.rotations)
     tr.build_acceleration_structure(v, f, rebuild=True)
+    gen = torch.Generator(device="cpu").manual_seed(123)
     ro = torch.zeros(16, 16, 3, device="cuda")
-    rd = torch.randn(16, 16, 3, device="cuda")
+    rd = torch.randn(16, 16, 3, generator=gen).cuda()
     rd[0, 0] = 0.0                       # zero direction
     rd[0, 1] = float("nan")              # NaN direction
     rd[0, 2] = torch.tensor([1.0, 0.0, 0.0])   # axis-aligned
@@ -99,9 +100,9 @@ def test_degenerate_rays_and_refit(built_lib):
     rgb = out[0]
     assert torch.isfinite(rgb[1:]).all() and float(out[2][0, 0]) == 0.0
     # refit (rebuild=0) after moving the surfels must equal a fresh build
-    means2 = env.means + 0.05 * torch.randn_like(env.means)
+    means2 = env.means + 0.05 * torch.randn(env.means.shape, generator=gen).cuda()
     v2, f2 = scene.quad_vertices(means2, env.scales, env.rotations)
-    rd = torch.randn(16, 16, 3, device="cuda")
+    rd = torch.randn(16, 16, 3, generator=gen).cuda()
     tr.build_acceleration_structure(v2, f2, rebuild=False)
     a = tr(ro, rd, v2, means2, torch.zeros_like(means2), shs=env.shs, opacities=env.opacities, scales=env.scales,
            rotations=env.rotations, tracer_settings=s, start_from_first=False)
