@@ -51,6 +51,8 @@ int mark_visible_impl(int P, const float* means3D, const float* viewmatrix, uint
 int trace_forward_impl(Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_out& o, cudaStream_t stream);
 int trace_backward_impl(Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_grads& g, cudaStream_t stream);
 size_t trace_cache_bytes(int H, int W);
+int sh_features_forward_impl(int P, int D, int M, int E, const float* means, const float* shs, const float* extra, const float* campos, float* out, cudaStream_t stream);
+int sh_features_backward_impl(int P, int D, int M, int E, const float* means, const float* shs, const float* campos, const float* dL_dout, float* dL_dmeans, float* dL_dshs, float* dL_dextra, cudaStream_t stream);
 bool trace_fast_eligible(const envgs_trace_args& a, const void* cache);
 struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; };
 int trace_forward_fast(Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_out& o, void* cache, cudaStream_t stream, const SideStream& side);
@@ -197,6 +199,25 @@ void envgs_tracer_destroy(envgs_tracer* h) {
 size_t envgs_tracer_bvh_bytes(int32_t P) { return lbvh_storage_bytes(P); }
 
 size_t envgs_trace_cache_bytes(int32_t H, int32_t W) { return trace_cache_bytes(H, W); }
+
+static int check_features(int32_t P, int32_t D, int32_t M, int32_t E) {
+    if (P < 0 || E < 0 || D < 0 || D > 3 || (D + 1) * (D + 1) > M) { set_error("bad sh_features arguments P=%d D=%d M=%d E=%d", P, D, M, E); return ENVGS_ERR_INVALID; }
+    return ENVGS_OK;
+}
+int envgs_sh_features_forward(int32_t P, int32_t D, int32_t M, int32_t E, const float* means3D, const float* shs, const float* extra,
+                              const float* campos, float* out, void* stream) {
+    int rc = check_features(P, D, M, E);
+    if (rc != ENVGS_OK) return rc;
+    if (P > 0 && (!means3D || !shs || !campos || !out || (E > 0 && !extra))) { set_error("sh_features pointer is NULL"); return ENVGS_ERR_INVALID; }
+    return sh_features_forward_impl(P, D, M, E, means3D, shs, extra, campos, out, (cudaStream_t)stream);
+}
+int envgs_sh_features_backward(int32_t P, int32_t D, int32_t M, int32_t E, const float* means3D, const float* shs, const float* campos,
+                               const float* dL_dout, float* dL_dmeans3D, float* dL_dshs, float* dL_dextra, void* stream) {
+    int rc = check_features(P, D, M, E);
+    if (rc != ENVGS_OK) return rc;
+    if (P > 0 && (!means3D || !shs || !campos || !dL_dout || !dL_dmeans3D || !dL_dshs || (E > 0 && !dL_dextra))) { set_error("sh_features pointer is NULL"); return ENVGS_ERR_INVALID; }
+    return sh_features_backward_impl(P, D, M, E, means3D, shs, campos, dL_dout, dL_dmeans3D, dL_dshs, dL_dextra, (cudaStream_t)stream);
+}
 
 int envgs_debug_trace_stats(envgs_tracer* h, int32_t enable, uint64_t out[8]) {
     if (!h) { set_error("tracer handle is NULL"); return ENVGS_ERR_INVALID; }

@@ -1,0 +1,104 @@
+// features.cu — fused "SH -> view-dependent RGB, clamp, append specular/roughness" for the base surfels, with backward.
+//
+// SURVEY.md §8(f) rank 1 (glue on the caller's side of the rasterizer): EnvGS evaluates the base colours in PyTorch
+// (EVC/utils/gaussian2d_utils.py:1071-1084: eval_sh + clamp_min(+0.5) + cat[specular, roughness]) because the C = 5
+// rasterizer only takes precomputed colours.  In eager PyTorch that is ~60 element-wise launches forward and, in backward,
+// sixteen select_backward + add_ passes over the (P,16,3) coefficient tensor (~9 GB of traffic at 1 M surfels).
+// Here: one pass each way, 192 B of coefficients read once per surfel.
+#include "common.cuh"
+
+namespace envgs {
+
+__device__ __forceinline__ float3 sh_basis_grad_k(int k, float3 d) {
+    const float x = d.x, y = d.y, z = d.z;
+    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+    switch (k) {
+        case 1: return f3(0.0f, -SH_C1, 0.0f);
+        case 2: return f3(0.0f, 0.0f, SH_C1);
+        case 3: return f3(-SH_C1, 0.0f, 0.0f);
+        case 4: return SH_C2[0] * f3(y, x, 0.0f);
+        case 5: return SH_C2[1] * f3(0.0f, z, y);
+        case 6: return SH_C2[2] * f3(-2.0f * x, -2.0f * y, 4.0f * z);
+        case 7: return SH_C2[3] * f3(z, 0.0f, x);
+        case 8: return SH_C2[4] * f3(2.0f * x, -2.0f * y, 0.0f);
+        case 9: return SH_C3[0] * f3(6.0f * xy, 3.0f * xx - 3.0f * yy, 0.0f);
+        case 10: return SH_C3[1] * f3(yz, xz, xy);
+        case 11: return SH_C3[2] * f3(-2.0f * xy, 4.0f * zz - xx - 3.0f * yy, 8.0f * yz);
+        case 12: return SH_C3[3] * f3(-6.0f * xz, -6.0f * yz, 6.0f * zz - 3.0f * xx - 3.0f * yy);
+        case 13: return SH_C3[4] * f3(4.0f * zz - 3.0f * xx - yy, -2.0f * xy, 8.0f * xz);
+        case 14: return SH_C3[5] * f3(2.0f * xz, -2.0f * yz, xx - yy);
+        case 15: return SH_C3[6] * f3(3.0f * xx - 3.0f * yy, -6.0f * xy, 0.0f);
+        default: return f3(0.0f, 0.0f, 0.0f);
+    }
+}
+
+// out (P, 3 + E): rgb | extra (E columns copied from `extra`, e.g. specular, roughness)
+__global__ void __launch_bounds__(256) sh_features_fwd_kernel(int P, int D, int M, int E, const float* __restrict__ means,
+                                                              const float* __restrict__ shs, const float* __restrict__ extra,
+                                                              const float* __restrict__ campos, float* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    float3 dir = ld3(means, i) - f3(campos[0], campos[1], campos[2]);
+    dir = dir / fmaxf(length3(dir), 1e-12f);   // F.normalize's eps
+    float b[16];
+    sh_basis(D, dir, b);
+    const int nb = (D + 1) * (D + 1);
+    const float* sh = shs + (size_t)i * M * 3;
+    float3 res = f3(0, 0, 0);
+    for (int k = 0; k < nb; k++) res += b[k] * f3(sh[3 * k], sh[3 * k + 1], sh[3 * k + 2]);
+    float* o = out + (size_t)i * (3 + E);
+    o[0] = fmaxf(res.x + 0.5f, 0.0f); o[1] = fmaxf(res.y + 0.5f, 0.0f); o[2] = fmaxf(res.z + 0.5f, 0.0f);
+    for (int e = 0; e < E; e++) o[3 + e] = extra[(size_t)i * E + e];
+}
+
+__global__ void __launch_bounds__(256) sh_features_bwd_kernel(int P, int D, int M, int E, const float* __restrict__ means,
+                                                              const float* __restrict__ shs, const float* __restrict__ campos,
+                                                              const float* __restrict__ dL_dout, float* __restrict__ dL_dmeans,
+                                                              float* __restrict__ dL_dshs, float* __restrict__ dL_dextra) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const float3 dir_orig = ld3(means, i) - f3(campos[0], campos[1], campos[2]);
+    const float len = fmaxf(length3(dir_orig), 1e-12f);
+    const float3 dir = dir_orig / len;
+    float b[16];
+    sh_basis(D, dir, b);
+    const int nb = (D + 1) * (D + 1);
+    const float* sh = shs + (size_t)i * M * 3;
+    float3 res = f3(0, 0, 0);
+    for (int k = 0; k < nb; k++) res += b[k] * f3(sh[3 * k], sh[3 * k + 1], sh[3 * k + 2]);
+    const float* g = dL_dout + (size_t)i * (3 + E);
+    // clamp_min(x + 0.5, 0): gradient passes where the pre-clamp value is >= 0
+    const float3 dRGB = f3(res.x + 0.5f >= 0.0f ? g[0] : 0.0f, res.y + 0.5f >= 0.0f ? g[1] : 0.0f, res.z + 0.5f >= 0.0f ? g[2] : 0.0f);
+    float* dsh = dL_dshs + (size_t)i * M * 3;
+    float3 dL_ddir = f3(0, 0, 0);
+    for (int k = 0; k < M; k++) {
+        const float bk = k < nb ? b[k] : 0.0f;
+        dsh[3 * k] = bk * dRGB.x; dsh[3 * k + 1] = bk * dRGB.y; dsh[3 * k + 2] = bk * dRGB.z;
+        if (k < nb) {
+            const float u = sh[3 * k] * dRGB.x + sh[3 * k + 1] * dRGB.y + sh[3 * k + 2] * dRGB.z;
+            dL_ddir += u * sh_basis_grad_k(k, dir);
+        }
+    }
+    const float3 dm = dnormvdv(dir_orig, dL_ddir);
+    dL_dmeans[3 * (size_t)i] = dm.x; dL_dmeans[3 * (size_t)i + 1] = dm.y; dL_dmeans[3 * (size_t)i + 2] = dm.z;
+    for (int e = 0; e < E; e++) dL_dextra[(size_t)i * E + e] = g[3 + e];
+}
+
+int sh_features_forward_impl(int P, int D, int M, int E, const float* means, const float* shs, const float* extra, const float* campos,
+                             float* out, cudaStream_t stream) {
+    if (P <= 0) return ENVGS_OK;
+    ENVGS_TIMED("sh_features_fwd", stream);
+    sh_features_fwd_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, D, M, E, means, shs, extra, campos, out);
+    ENVGS_LAUNCH_CHECK("sh_features_fwd", false, stream);
+    return ENVGS_OK;
+}
+int sh_features_backward_impl(int P, int D, int M, int E, const float* means, const float* shs, const float* campos, const float* dL_dout,
+                              float* dL_dmeans, float* dL_dshs, float* dL_dextra, cudaStream_t stream) {
+    if (P <= 0) return ENVGS_OK;
+    ENVGS_TIMED("sh_features_bwd", stream);
+    sh_features_bwd_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, D, M, E, means, shs, campos, dL_dout, dL_dmeans, dL_dshs, dL_dextra);
+    ENVGS_LAUNCH_CHECK("sh_features_bwd", false, stream);
+    return ENVGS_OK;
+}
+
+}  // namespace envgs

@@ -17,6 +17,7 @@ import torch
 import torch.nn as nn
 
 from . import scene
+from .features import sh_features
 from .rasterizer import GaussianRasterizationSettings, make_module
 from .tracer import SurfelTracer, SurfelTracingSettings
 
@@ -64,8 +65,9 @@ def depth_to_normal(cam: scene.Camera, dpt: torch.Tensor) -> torch.Tensor:
 class EnvGSRenderer(nn.Module):
     """Holds the base and environment surfel sets as parameters and renders / differentiates one view."""
 
-    def __init__(self, base: scene.SurfelSet, env: scene.SurfelSet | None, device="cuda"):
+    def __init__(self, base: scene.SurfelSet, env: scene.SurfelSet | None, device="cuda", fused_features: bool = True):
         super().__init__()
+        self.fused_features = fused_features   # False: evaluate the base SH colours in PyTorch exactly like the reference
         dev = torch.device(device)
         P = lambda t: nn.Parameter(t.to(dev).contiguous())
         self.means, self.scales, self.rotations, self.opacities = P(base.means), P(base.scales), P(base.rotations), P(base.opacities)
@@ -82,14 +84,21 @@ class EnvGSRenderer(nn.Module):
     def rasterize_base(self, cam: scene.Camera) -> dict:
         settings = GaussianRasterizationSettings(cam.H, cam.W, cam.tanfovx, cam.tanfovy, self.bg, 1.0, cam.viewmatrix,
                                                  cam.projmatrix, 3, cam.campos, False, False)
-        dirs = torch.nn.functional.normalize(self.means - cam.campos[None], dim=-1)
-        rgb = torch.clamp_min(eval_sh_deg3(self.shs, dirs) + 0.5, 0.0)
-        colors = torch.cat([rgb, self.specular, self.roughness], dim=-1)
+        if self.fused_features:
+            colors = sh_features(self.means, self.shs, torch.cat([self.specular, self.roughness], dim=-1), cam.campos, 3)
+        else:
+            dirs = torch.nn.functional.normalize(self.means - cam.campos[None], dim=-1)
+            rgb = torch.clamp_min(eval_sh_deg3(self.shs, dirs) + 0.5, 0.0)
+            colors = torch.cat([rgb, self.specular, self.roughness], dim=-1)
         means2D = torch.zeros_like(self.means, requires_grad=True)
         image, radii, allmap, weight = _Rasterizer5(settings)(means3D=self.means, means2D=means2D, opacities=self.opacities,
                                                               colors_precomp=colors, scales=self.scales, rotations=self.rotations)
         alpha = allmap[1:2]
-        normal = (allmap[2:5].permute(1, 2, 0) @ cam.viewmatrix[:3, :3].t()).permute(2, 0, 1)   # view -> world
+        Rv = cam.viewmatrix[:3, :3]                                                              # view -> world: n_w = Rv n_v
+        nv = allmap[2:5]
+        normal = torch.stack([Rv[0, 0] * nv[0] + Rv[0, 1] * nv[1] + Rv[0, 2] * nv[2],
+                              Rv[1, 0] * nv[0] + Rv[1, 1] * nv[1] + Rv[1, 2] * nv[2],
+                              Rv[2, 0] * nv[0] + Rv[2, 1] * nv[1] + Rv[2, 2] * nv[2]], dim=0)
         depth = torch.nan_to_num(allmap[0:1] / alpha, 0.0, 0.0)                                  # depth_ratio = 0
         surf_normal = depth_to_normal(cam, depth).permute(2, 0, 1) * alpha.detach()
         return dict(render=image[:3], specular=image[3:4], roughness=image[4:5], alpha=alpha, normal=normal, depth=depth,

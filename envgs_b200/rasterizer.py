@@ -128,10 +128,13 @@ def make_module(C_channels: int):
             bg = _pad_bg(s.bg, C_channels, device)
             vm, pm, cam = _f32c(s.viewmatrix, device), _f32c(s.projmatrix, device), _f32c(s.campos, device)
 
-            color = torch.zeros((C_channels, H, W), dtype=torch.float32, device=device)
-            others = torch.zeros((7, H, W), dtype=torch.float32, device=device)
+            # every pixel / every radius is written by the kernels (P == 0 excepted); only the atomically accumulated
+            # blend weights need a zero fill
+            alloc = torch.empty if P > 0 else torch.zeros
+            color = alloc((C_channels, H, W), dtype=torch.float32, device=device)
+            others = alloc((7, H, W), dtype=torch.float32, device=device)
             weight = torch.zeros((P, 1), dtype=torch.float32, device=device)
-            radii = torch.zeros((P,), dtype=torch.int32, device=device)
+            radii = alloc((P,), dtype=torch.int32, device=device)
             scratch = _Scratch(device)
 
             args = _make_args(C_channels, s, bg, m3, shc, col, opa, sc, rot, cov, vm, pm, cam)

@@ -133,8 +133,9 @@ class _TraceSurfels(torch.autograd.Function):
         vm, pm, cam = _f32c(s.viewmatrix, device), _f32c(s.projmatrix, device), _f32c(s.campos, device)
 
         f = dict(dtype=torch.float32, device=device)
-        out_rgb, out_dpt, out_acc = torch.zeros((H, W, 3), **f), torch.zeros((H, W, 1), **f), torch.zeros((H, W, 1), **f)
-        out_norm, out_dist, out_aux = torch.zeros((H, W, 3), **f), torch.zeros((H, W, 3), **f), torch.zeros((H, W, AUX_CHANNELS), **f)
+        # every ray's outputs are written by the kernels
+        out_rgb, out_dpt, out_acc = torch.empty((H, W, 3), **f), torch.empty((H, W, 1), **f), torch.empty((H, W, 1), **f)
+        out_norm, out_dist, out_aux = torch.empty((H, W, 3), **f), torch.empty((H, W, 3), **f), torch.empty((H, W, AUX_CHANNELS), **f)
         mid_val = torch.empty((H, W, MID_CHANNELS * (MAX_TRACE_DEPTH + 1)), **f)   # fully written by the kernel
         a_weights = torch.zeros((P, 1), **f) if training else None
         # scratch for the hit-parallel fast path (per-ray hit lists, re-used by backward); the library falls back to the

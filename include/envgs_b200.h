@@ -202,6 +202,18 @@ typedef struct envgs_trace_grads {
 int envgs_trace_backward(envgs_tracer* h, const envgs_trace_args* args, const envgs_trace_grads* grads,
                          void* stream);
 
+/* ------------------------------------------------------------------------------------------------ */
+/* Caller-side glue: base-surfel features for the C = 5 / 7 rasterizer          */
+/* ------------------------------------------------------------------------------------------------ */
+/* out (P, 3+E) = [ max(SH_D(normalize(mean - campos)) + 0.5, 0) | extra (P,E) ]  — what EasyVolcap computes in PyTorch
+ * at easyvolcap/utils/gaussian2d_utils.py:1071-1084 (eval_sh, clamp_min, cat[specular, roughness]). */
+int envgs_sh_features_forward(int32_t P, int32_t sh_degree, int32_t sh_coeffs, int32_t E, const float* means3D, const float* shs,
+                              const float* extra, const float* campos, float* out, void* stream);
+/* all three gradient outputs are fully written (no zero-fill needed) */
+int envgs_sh_features_backward(int32_t P, int32_t sh_degree, int32_t sh_coeffs, int32_t E, const float* means3D, const float* shs,
+                               const float* campos, const float* dL_dout, float* dL_dmeans3D, float* dL_dshs, float* dL_dextra,
+                               void* stream);
+
 /* Kernel-launch counter (every kernel this library launches increments it); bench.py reports it. */
 uint64_t envgs_launch_count(void);
 

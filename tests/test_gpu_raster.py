@@ -150,3 +150,24 @@ def test_full_hd_properties(built_lib):
     cu2 = Hh.run_cuda_raster(base, cam, 5, feats=feats, g_color=2 * gc, g_others=2 * go)
     assert Hh.rel_l2(cu2["g_colors"], 2 * cu["g_colors"]) < 1e-4
     assert Hh.rel_l2(cu2["g_means"], 2 * cu["g_means"]) < 1e-3
+
+
+def test_fused_sh_features_match_pytorch(built_lib):
+    """envgs_sh_features_* (caller-side glue) vs the PyTorch expressions EasyVolcap uses."""
+    from envgs_b200.features import sh_features
+    from envgs_b200.pipeline import eval_sh_deg3
+    base = scene.make_base_set(20000, seed=3).to("cuda")
+    cam = scene.ring_cameras(1, 64, 64)[0].to("cuda")
+    leaf = lambda t: t.clone().requires_grad_(True)
+    m1, s1, e1 = leaf(base.means), leaf(base.shs * 3.0), leaf(torch.cat([base.specular, base.roughness], -1))   # x3: exercise the clamp
+    out = sh_features(m1, s1, e1, cam.campos, 3)
+    m2, s2, e2 = leaf(base.means), leaf(base.shs * 3.0), leaf(torch.cat([base.specular, base.roughness], -1))
+    dirs = torch.nn.functional.normalize(m2 - cam.campos[None], dim=-1)
+    ref = torch.cat([torch.clamp_min(eval_sh_deg3(s2, dirs) + 0.5, 0.0), e2], dim=-1)
+    assert float((out - ref).abs().max()) < 1e-5
+    assert float((ref[:, :3] == 0).float().mean()) > 0.01          # some channels are clamped
+    g = torch.randn_like(ref)
+    (out * g).sum().backward()
+    (ref * g).sum().backward()
+    assert Hh.rel_l2(s1.grad, s2.grad) < 1e-5 and Hh.rel_l2(e1.grad, e2.grad) < 1e-6
+    assert Hh.trimmed_rel_l2(m1.grad, m2.grad) < 1e-4
