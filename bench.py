@@ -51,50 +51,62 @@ def parse_args():
 # clocks sampling (B200_PROFILING.md recipe)
 # ---------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled DURING the timed region through NVML (a few microseconds per query; an
+    `nvidia-smi -lms` loop holds driver locks long enough to stall this launch-heavy step)."""
 
-    def __init__(self, gpu_index: int):
-        self.gpu = gpu_index
-        self.proc = None
-        self.lines = []
+    def __init__(self, gpu_index: int, period_s: float = 0.2):
+        self.gpu, self.period = gpu_index, period_s
+        self.samples, self.reasons, self.max_clock = [], set(), None
+        self._stop = threading.Event()
+        self.thread = None
+        self.err = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu]) if vis and vis.split(",")[self.gpu].isdigit() else self.gpu
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nv = pynvml
+            self.max_clock = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as ex:  # no NVML: report it instead of inventing numbers
+            self.err = f"nvml unavailable: {ex}"
+            return
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _run(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8)): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)): "sw_power_cap",
+        }
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                mask = int(get_reasons(self.h))
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception as ex:
+                self.err = str(ex)
+                return
+            self._stop.wait(self.period)
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            parts = [p.strip() for p in ln.split(",")]
-            if len(parts) < 9:
-                continue
-            try:
-                sm.append(float(parts[1])); mx.append(float(parts[2]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        self._stop.set()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        sm = sorted(self.samples)
+        out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_clock, "reasons": sorted(self.reasons),
+               "samples": len(sm)}
+        if self.err:
+            out["note"] = self.err
+        return out
 
 
 def measured_peaks() -> tuple[float, str]:
@@ -306,7 +318,7 @@ def main():
         for s in range(nprof):
             cam = dev_cams[s % len(dev_cams)]
             trainer.flat.zero_grad()
-            out = renderer(cam)
+            out = renderer(cam, target_dev)
             renderer.loss(out, target_dev).backward()
             torch.cuda.synchronize()
             stats.append((int((out["radii"] > 0).sum()),))

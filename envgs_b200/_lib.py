@@ -51,6 +51,10 @@ class TraceArgs(C.Structure):
     ]
 
 
+class GlueCamera(C.Structure):
+    _fields_ = [("H", C.c_int32), ("W", C.c_int32), ("tanfovx", C.c_float), ("tanfovy", C.c_float), ("K", _fp), ("R", _fp), ("campos", _fp)]
+
+
 class TraceOut(C.Structure):
     _fields_ = [("out_rgb", _fp), ("out_dpt", _fp), ("out_acc", _fp), ("out_norm", _fp), ("out_dist", _fp),
                 ("out_aux", _fp), ("mid_val", _fp), ("a_weights", _fp), ("hit_cache", _fp)]
@@ -72,6 +76,7 @@ EXPORTS = [
     "envgs_raster_geom_bytes", "envgs_raster_img_bytes", "envgs_raster_binning_bytes", "envgs_tracer_create",
     "envgs_tracer_destroy", "envgs_tracer_build", "envgs_tracer_bvh_bytes", "envgs_trace_forward",
     "envgs_trace_backward", "envgs_launch_count", "envgs_profile_enable", "envgs_profile_report", "envgs_debug_trace_stats", "envgs_trace_cache_bytes", "envgs_sh_features_forward", "envgs_sh_features_backward",
+    "envgs_glue_reflect_forward", "envgs_glue_reflect_backward", "envgs_glue_blend_loss_forward", "envgs_glue_blend_loss_backward",
 ]
 
 _lib = None
@@ -122,6 +127,14 @@ def lib() -> C.CDLL:
     L.envgs_sh_features_forward.argtypes = [C.c_int32] * 4 + [C.c_void_p] * 6
     L.envgs_sh_features_backward.restype = C.c_int
     L.envgs_sh_features_backward.argtypes = [C.c_int32] * 4 + [C.c_void_p] * 8
+    L.envgs_glue_reflect_forward.restype = C.c_int
+    L.envgs_glue_reflect_forward.argtypes = [C.POINTER(GlueCamera)] + [C.c_void_p] * 4
+    L.envgs_glue_reflect_backward.restype = C.c_int
+    L.envgs_glue_reflect_backward.argtypes = [C.POINTER(GlueCamera)] + [C.c_void_p] * 5
+    L.envgs_glue_blend_loss_forward.restype = C.c_int
+    L.envgs_glue_blend_loss_forward.argtypes = [C.POINTER(GlueCamera)] + [C.c_void_p] * 4 + [C.c_float] + [C.c_void_p] * 3
+    L.envgs_glue_blend_loss_backward.restype = C.c_int
+    L.envgs_glue_blend_loss_backward.argtypes = [C.POINTER(GlueCamera)] + [C.c_void_p] * 5 + [C.c_float] + [C.c_void_p] * 6
     L.envgs_debug_trace_stats.restype = C.c_int
     L.envgs_debug_trace_stats.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_uint64)]
     _lib = L

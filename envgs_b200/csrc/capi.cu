@@ -51,6 +51,10 @@ int mark_visible_impl(int P, const float* means3D, const float* viewmatrix, uint
 int trace_forward_impl(Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_out& o, cudaStream_t stream);
 int trace_backward_impl(Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_grads& g, cudaStream_t stream);
 size_t trace_cache_bytes(int H, int W);
+int glue_reflect_forward(const envgs_glue_camera& cam, const float* allmap, float* ref_o, float* ref_d, cudaStream_t stream);
+int glue_reflect_backward(const envgs_glue_camera& cam, const float* allmap, const float* g_ro, const float* g_rd, float* dL_dallmap, cudaStream_t stream);
+int glue_blend_loss_forward(const envgs_glue_camera& cam, const float* image, const float* allmap, const float* env_rgb, const float* target, float lambda_n, float* rgb_out, float* loss2, cudaStream_t stream);
+int glue_blend_loss_backward(const envgs_glue_camera& cam, const float* image, const float* allmap, const float* env_rgb, const float* target, const float* rgb, float lambda_n, const float* g_loss, const float* g_rgb, float* dL_dimage, float* dL_dallmap, float* dL_denv, cudaStream_t stream);
 int sh_features_forward_impl(int P, int D, int M, int E, const float* means, const float* shs, const float* extra, const float* campos, float* out, cudaStream_t stream);
 int sh_features_backward_impl(int P, int D, int M, int E, const float* means, const float* shs, const float* campos, const float* dL_dout, float* dL_dmeans, float* dL_dshs, float* dL_dextra, cudaStream_t stream);
 bool trace_fast_eligible(const envgs_trace_args& a, const void* cache);
@@ -199,6 +203,39 @@ void envgs_tracer_destroy(envgs_tracer* h) {
 size_t envgs_tracer_bvh_bytes(int32_t P) { return lbvh_storage_bytes(P); }
 
 size_t envgs_trace_cache_bytes(int32_t H, int32_t W) { return trace_cache_bytes(H, W); }
+
+static int check_glue_cam(const envgs_glue_camera* c) {
+    if (!c || c->H <= 0 || c->W <= 0 || !c->K || !c->R || !c->campos) { set_error("bad glue camera"); return ENVGS_ERR_INVALID; }
+    return ENVGS_OK;
+}
+int envgs_glue_reflect_forward(const envgs_glue_camera* cam, const float* allmap, float* ref_o, float* ref_d, void* stream) {
+    int rc = check_glue_cam(cam);
+    if (rc != ENVGS_OK) return rc;
+    if (!allmap || !ref_o || !ref_d) { set_error("glue pointer is NULL"); return ENVGS_ERR_INVALID; }
+    return glue_reflect_forward(*cam, allmap, ref_o, ref_d, (cudaStream_t)stream);
+}
+int envgs_glue_reflect_backward(const envgs_glue_camera* cam, const float* allmap, const float* g_ro, const float* g_rd, float* dL_dallmap,
+                                void* stream) {
+    int rc = check_glue_cam(cam);
+    if (rc != ENVGS_OK) return rc;
+    if (!allmap || !g_ro || !g_rd || !dL_dallmap) { set_error("glue pointer is NULL"); return ENVGS_ERR_INVALID; }
+    return glue_reflect_backward(*cam, allmap, g_ro, g_rd, dL_dallmap, (cudaStream_t)stream);
+}
+int envgs_glue_blend_loss_forward(const envgs_glue_camera* cam, const float* image, const float* allmap, const float* env_rgb,
+                                  const float* target, float lambda_n, float* rgb_out, float* loss2, void* stream) {
+    int rc = check_glue_cam(cam);
+    if (rc != ENVGS_OK) return rc;
+    if (!image || !allmap || !target || !rgb_out || !loss2) { set_error("glue pointer is NULL"); return ENVGS_ERR_INVALID; }
+    return glue_blend_loss_forward(*cam, image, allmap, env_rgb, target, lambda_n, rgb_out, loss2, (cudaStream_t)stream);
+}
+int envgs_glue_blend_loss_backward(const envgs_glue_camera* cam, const float* image, const float* allmap, const float* env_rgb,
+                                   const float* target, const float* rgb, float lambda_n, const float* g_loss, const float* g_rgb,
+                                   float* dL_dimage, float* dL_dallmap, float* dL_denv, void* stream) {
+    int rc = check_glue_cam(cam);
+    if (rc != ENVGS_OK) return rc;
+    if (!image || !allmap || !target || !rgb || !g_loss || !dL_dimage || !dL_dallmap || (env_rgb && !dL_denv)) { set_error("glue pointer is NULL"); return ENVGS_ERR_INVALID; }
+    return glue_blend_loss_backward(*cam, image, allmap, env_rgb, target, rgb, lambda_n, g_loss, g_rgb, dL_dimage, dL_dallmap, dL_denv, (cudaStream_t)stream);
+}
 
 static int check_features(int32_t P, int32_t D, int32_t M, int32_t E) {
     if (P < 0 || E < 0 || D < 0 || D > 3 || (D + 1) * (D + 1) > M) { set_error("bad sh_features arguments P=%d D=%d M=%d E=%d", P, D, M, E); return ENVGS_ERR_INVALID; }

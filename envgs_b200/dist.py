@@ -86,7 +86,7 @@ class ViewParallelTrainer:
 
     def step(self, cam, target) -> torch.Tensor:
         self.flat.zero_grad()
-        out = self.renderer(cam)
+        out = self.renderer(cam, target)
         loss = self.renderer.loss(out, target)
         loss.backward()
         self.flat.collect_stray_grads()

@@ -17,6 +17,7 @@ import torch
 import torch.nn as nn
 
 from . import scene
+from . import glue
 from .features import sh_features
 from .rasterizer import GaussianRasterizationSettings, make_module
 from .tracer import SurfelTracer, SurfelTracingSettings
@@ -65,9 +66,12 @@ def depth_to_normal(cam: scene.Camera, dpt: torch.Tensor) -> torch.Tensor:
 class EnvGSRenderer(nn.Module):
     """Holds the base and environment surfel sets as parameters and renders / differentiates one view."""
 
-    def __init__(self, base: scene.SurfelSet, env: scene.SurfelSet | None, device="cuda", fused_features: bool = True):
+    def __init__(self, base: scene.SurfelSet, env: scene.SurfelSet | None, device="cuda", fused_features: bool = True,
+                 fused_glue: bool = True):
         super().__init__()
         self.fused_features = fused_features   # False: evaluate the base SH colours in PyTorch exactly like the reference
+        self.fused_glue = fused_glue           # False: per-pixel glue (reflection, dpt2norm, blend, loss) in PyTorch like the reference
+        self.lambda_normal = 0.04
         dev = torch.device(device)
         P = lambda t: nn.Parameter(t.to(dev).contiguous())
         self.means, self.scales, self.rotations, self.opacities = P(base.means), P(base.scales), P(base.rotations), P(base.opacities)
@@ -81,7 +85,7 @@ class EnvGSRenderer(nn.Module):
         self.register_buffer("env_bg", torch.zeros(3, device=dev))
 
     # ---- base pass -------------------------------------------------------------------------------------------
-    def rasterize_base(self, cam: scene.Camera) -> dict:
+    def _raster(self, cam: scene.Camera):
         settings = GaussianRasterizationSettings(cam.H, cam.W, cam.tanfovx, cam.tanfovy, self.bg, 1.0, cam.viewmatrix,
                                                  cam.projmatrix, 3, cam.campos, False, False)
         if self.fused_features:
@@ -93,6 +97,10 @@ class EnvGSRenderer(nn.Module):
         means2D = torch.zeros_like(self.means, requires_grad=True)
         image, radii, allmap, weight = _Rasterizer5(settings)(means3D=self.means, means2D=means2D, opacities=self.opacities,
                                                               colors_precomp=colors, scales=self.scales, rotations=self.rotations)
+        return image, radii, allmap, weight, means2D
+
+    def rasterize_base(self, cam: scene.Camera) -> dict:
+        image, radii, allmap, weight, means2D = self._raster(cam)
         alpha = allmap[1:2]
         Rv = cam.viewmatrix[:3, :3]                                                              # view -> world: n_w = Rv n_v
         nv = allmap[2:5]
@@ -102,7 +110,7 @@ class EnvGSRenderer(nn.Module):
         depth = torch.nan_to_num(allmap[0:1] / alpha, 0.0, 0.0)                                  # depth_ratio = 0
         surf_normal = depth_to_normal(cam, depth).permute(2, 0, 1) * alpha.detach()
         return dict(render=image[:3], specular=image[3:4], roughness=image[4:5], alpha=alpha, normal=normal, depth=depth,
-                    surf_normal=surf_normal, dist=allmap[6:7], radii=radii, weight=weight, means2D=means2D)
+                    surf_normal=surf_normal, dist=allmap[6:7], radii=radii, weight=weight, means2D=means2D, image=image, allmap=allmap)
 
     # ---- environment pass ------------------------------------------------------------------------------------
     def trace_env(self, cam: scene.Camera, ref_o: torch.Tensor, ref_d: torch.Tensor) -> dict:
@@ -118,7 +126,9 @@ class EnvGSRenderer(nn.Module):
                                                                start_from_first=False)
         return dict(rgb=rgb, dpt=dpt, acc=acc, norm=norm, wet=wet, grads3D=grads3D)
 
-    def forward(self, cam: scene.Camera) -> dict:
+    def forward(self, cam: scene.Camera, target: torch.Tensor | None = None) -> dict:
+        if self.fused_glue and target is not None:
+            return self._forward_fused(cam, target)
         out = self.rasterize_base(cam)
         rgb = out["render"].permute(1, 2, 0)                     # (H,W,3)
         if self.has_env:
@@ -134,11 +144,26 @@ class EnvGSRenderer(nn.Module):
         out["rgb"] = rgb
         return out
 
+    def _forward_fused(self, cam: scene.Camera, target: torch.Tensor) -> dict:
+        """Same computation with the per-pixel glue in two fused kernels per direction (envgs_b200/glue.py)."""
+        image, radii, allmap, weight, means2D = self._raster(cam)
+        env = None
+        if self.has_env:
+            ref_o, ref_d = glue.reflect_rays(allmap, cam)
+            env = self.trace_env(cam, ref_o, ref_d)
+        rgb, loss, parts = glue.blend_loss(image, allmap, None if env is None else env["rgb"], target, cam, self.lambda_normal)
+        out = dict(rgb=rgb, loss=loss, loss_parts=parts, radii=radii, weight=weight, means2D=means2D, image=image, allmap=allmap)
+        if env is not None:
+            out["env"] = env
+        return out
+
     def loss(self, out: dict, target: torch.Tensor) -> torch.Tensor:
         """L1 image loss + 0.04 normal-consistency, so colour, depth, alpha and normal grads are all non-zero."""
+        if "loss" in out:
+            return out["loss"]
         l1 = (out["rgb"] - target).abs().mean()
         ncons = (1.0 - (out["normal"] * out["surf_normal"]).sum(0)).mean()
-        return l1 + 0.04 * ncons
+        return l1 + self.lambda_normal * ncons
 
     def flat_grads(self) -> list[torch.Tensor]:
         return [p.grad for p in self.parameters() if p.grad is not None]

@@ -214,6 +214,31 @@ int envgs_sh_features_backward(int32_t P, int32_t sh_degree, int32_t sh_coeffs, 
                                const float* campos, const float* dL_dout, float* dL_dmeans3D, float* dL_dshs, float* dL_dextra,
                                void* stream);
 
+/* Per-pixel glue between the two operators, fused (reference: ~150 eager PyTorch launches per view —
+ * gaussian2d_utils.py:1117-1153 + :1158-1206, ray_utils.py:24-78, envgs_sampler.py:420-431 + :474, plus the loss). */
+typedef struct envgs_glue_camera {
+    int32_t H, W;
+    float tanfovx, tanfovy;
+    const float* K;       /* (3,3) row-major, device: intrinsics of the camera rays (pixel centres at +0.5) */
+    const float* R;       /* (3,3) row-major, device: world->camera rotation */
+    const float* campos;  /* (3,)  device */
+} envgs_glue_camera;
+
+/* allmap (7,H,W) -> reflected rays ref_o, ref_d (H,W,3):  depth = nan_to_num(D/alpha), n = R^T n_view / (|.|+1e-8),
+ * d' = d - 2 (d.n) n, o' = campos + depth d */
+int envgs_glue_reflect_forward(const envgs_glue_camera* cam, const float* allmap, float* ref_o, float* ref_d, void* stream);
+/* writes all 7 channels of dL_dallmap */
+int envgs_glue_reflect_backward(const envgs_glue_camera* cam, const float* allmap, const float* dL_dref_o, const float* dL_dref_d,
+                                float* dL_dallmap, void* stream);
+/* rgb (H,W,3) = (1-spec) base + spec env (env_rgb may be NULL: rgb = base);
+ * loss2[0] = mean|rgb - target|, loss2[1] = lambda_n * mean(1 - <n_world, alpha * dpt2norm(depth)>) */
+int envgs_glue_blend_loss_forward(const envgs_glue_camera* cam, const float* image, const float* allmap, const float* env_rgb,
+                                  const float* target, float lambda_n, float* rgb_out, float* loss2, void* stream);
+/* g_loss: (1,) upstream gradient of loss2[0]+loss2[1]; g_rgb optional (H,W,3); all outputs fully written */
+int envgs_glue_blend_loss_backward(const envgs_glue_camera* cam, const float* image, const float* allmap, const float* env_rgb,
+                                   const float* target, const float* rgb, float lambda_n, const float* g_loss, const float* g_rgb,
+                                   float* dL_dimage, float* dL_dallmap, float* dL_denv, void* stream);
+
 /* Kernel-launch counter (every kernel this library launches increments it); bench.py reports it. */
 uint64_t envgs_launch_count(void);
 

@@ -171,3 +171,25 @@ def test_fused_sh_features_match_pytorch(built_lib):
     (ref * g).sum().backward()
     assert Hh.rel_l2(s1.grad, s2.grad) < 1e-5 and Hh.rel_l2(e1.grad, e2.grad) < 1e-6
     assert Hh.trimmed_rel_l2(m1.grad, m2.grad) < 1e-4
+
+
+def test_fused_glue_matches_pytorch_pipeline(built_lib):
+    """Fused per-pixel glue (reflect + blend/loss kernels) vs the PyTorch expressions of the reference path, through the
+    whole per-view pipeline: same loss, same image, same parameter gradients."""
+    from envgs_b200.pipeline import EnvGSRenderer
+    base = scene.make_base_set(20000, seed=0, s0=0.02)
+    env = scene.make_env_set(4000, seed=1, s0=0.02)
+    cam = scene.ring_cameras(1, 120, 160, seed=2)[0].to("cuda")
+    target = torch.rand(120, 160, 3, generator=torch.Generator().manual_seed(3)).cuda()
+    res = {}
+    for fused in (False, True):
+        r = EnvGSRenderer(base, env, device="cuda", fused_features=fused, fused_glue=fused)
+        out = r(cam, target)
+        loss = r.loss(out, target)
+        loss.backward()
+        res[fused] = (float(loss), out["rgb"].detach().cpu(), {n: p.grad.detach().cpu() for n, p in r.named_parameters()})
+    assert abs(res[True][0] - res[False][0]) < 1e-5 * abs(res[False][0])
+    assert Hh.frac_above(res[True][1], res[False][1], 1e-5) < 1e-4
+    for n in res[False][2]:
+        t = Hh.trimmed_rel_l2(res[True][2][n], res[False][2][n])
+        assert t < 2e-3, f"{n}: {t:.3e} (full {Hh.rel_l2(res[True][2][n], res[False][2][n]):.3e})"

@@ -102,7 +102,7 @@ class _ToyRenderer(torch.nn.Module):
         self.a = torch.nn.Parameter(torch.randn(7, 3, generator=g))
         self.b = torch.nn.Parameter(torch.randn(5, generator=g))
 
-    def forward(self, cam):
+    def forward(self, cam, target=None):
         return {"rgb": (self.a * cam).sum() + (self.b ** 2).sum() * cam.mean()}
 
     def loss(self, out, target):

@@ -24,7 +24,7 @@ def main():
         _lib.lib().envgs_debug_trace_stats(r.tracer.optix_context.handle, 1, None)
     for s in range(steps):
         for p in r.parameters(): p.grad = None
-        out = r(cams[s % 4])
+        out = r(cams[s % 4], target)
         r.loss(out, target).backward()
     torch.cuda.synchronize()
     if stats and Pe:
@@ -34,7 +34,7 @@ def main():
         print(json.dumps({"ray_segments(fwd+bwd)": rays, "nodes/ray": nodes / rays, "quad_tests/ray": prims / rays, "hits_inserted/ray": hits / rays,
                           "chunks/ray": chunks / rays, "contributions/ray": contrib / rays}))
         acc = out["env"]["acc"]
-        print("env acc mean", float(acc.mean()), "spec mean", float(out["specular"].mean()), "alpha mean", float(out["alpha"].mean()))
+        print("env acc mean", float(acc.mean()), "alpha mean", float(out["allmap"][1].mean()))
 
 if __name__ == "__main__":
     main()

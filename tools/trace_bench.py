@@ -14,12 +14,12 @@ cam = scene.ring_cameras(4, H, W, seed=2)[0].to(dev)
 target = torch.rand(H, W, 3, device=dev)
 for it in range(3):
     for p in r.parameters(): p.grad = None
-    out = r(cam); r.loss(out, target).backward()
+    out = r(cam, target); r.loss(out, target).backward()
 torch.cuda.synchronize()
 _lib.profile_enable(True)
 for it in range(5):
     for p in r.parameters(): p.grad = None
-    out = r(cam); r.loss(out, target).backward()
+    out = r(cam, target); r.loss(out, target).backward()
 torch.cuda.synchronize()
 rep = _lib.profile_report()
 print(os.environ.get("ENVGS_TRACE_REFILL"), {k: round(v[1] / v[0], 3) for k, v in rep.items() if "trace" in k or "render" in k})
