@@ -243,12 +243,14 @@ __global__ void __launch_bounds__(256) collapse4_kernel(int n_internal, const Bv
     const int c[2] = {nodes[i].child0, nodes[i].child1};
     Bvh4Node out;
     int k = 0;
+    int leafmask = 0;   // which of the four slots hold surfels (replicated in every slot's b.w)
 #pragma unroll
     for (int s = 0; s < 2; s++) {
         if (c[s] < 0) {
             const float* b = nf + 6 * s;
             out.s[k].a = make_float4(b[0], b[1], b[2], b[3]);
             out.s[k].b = make_float4(b[4], b[5], __int_as_float(c[s]), 0.0f);
+            leafmask |= 1 << k;
             k++;
         } else {
             const float* cf = reinterpret_cast<const float*>(&nodes[c[s]]);
@@ -258,6 +260,7 @@ __global__ void __launch_bounds__(256) collapse4_kernel(int n_internal, const Bv
                 const float* b = cf + 6 * q;
                 out.s[k].a = make_float4(b[0], b[1], b[2], b[3]);
                 out.s[k].b = make_float4(b[4], b[5], __int_as_float(g[q]), 0.0f);
+                if (g[q] < 0) leafmask |= 1 << k;
                 k++;
             }
         }
@@ -265,7 +268,10 @@ __global__ void __launch_bounds__(256) collapse4_kernel(int n_internal, const Bv
     for (; k < 4; k++) {
         out.s[k].a = make_float4(FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX);
         out.s[k].b = make_float4(-FLT_MAX, -FLT_MAX, __int_as_float(~0), 0.0f);
+        leafmask |= 1 << k;
     }
+#pragma unroll
+    for (int q = 0; q < 4; q++) out.s[q].b.w = __int_as_float(leafmask);
     nodes4[i] = out;
 }
 

@@ -118,7 +118,8 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(
                 float3 l = pyf * Tw - Tv;
                 float3 p = cross(k, l);
                 if (p.z != 0.0f) {
-                    float sx = p.x / p.z, sy = p.y / p.z;
+                    const float rz = 1.0f / p.z;                 // same reciprocal form as the forward kernel
+                    float sx = p.x * rz, sy = p.y * rz;
                     float rho3d = sx * sx + sy * sy;
                     float dx = r2.y - pxf, dy = r2.z - pyf;
                     float rho2d = FILTER_INV_SQUARE * (dx * dx + dy * dy);
@@ -132,7 +133,8 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(
                         if (alpha >= ALPHA_MIN) {
                             contrib = true;
                             const float4 r3 = s_r3[j];
-                            T = T / (1.0f - alpha);
+                            const float r1ma = 1.0f / (1.0f - alpha);
+                            T = T * r1ma;
                             const float w = alpha * T;
                             float dL_dalpha = 0.0f;
 #pragma unroll
@@ -144,8 +146,9 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(
                                 g[ch] = w * dL_dpixel[ch];
                             }
                             float dL_dz = 0.0f, dL_dweight = 0.0f;
-                            const float m_d = FAR_N / (FAR_N - NEAR_N) * (1.0f - NEAR_N / c_d);
-                            const float dmd_dd = (FAR_N * NEAR_N) / ((FAR_N - NEAR_N) * c_d * c_d);
+                            const float rcd = 1.0f / c_d;
+                            const float m_d = FAR_N / (FAR_N - NEAR_N) * (1.0f - NEAR_N * rcd);
+                            const float dmd_dd = (FAR_N * NEAR_N) / (FAR_N - NEAR_N) * rcd * rcd;
                             if (pos == median_contributor) dL_dz += dL_dmedian_depth;
                             dL_dweight += (final_D2 + m_d * m_d * final_A - 2.0f * m_d * final_D) * dL_dreg;
                             dL_dalpha += dL_dweight - last_dL_dT;
@@ -168,7 +171,7 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(
 
                             dL_dalpha *= T;
                             last_alpha = alpha;
-                            dL_dalpha += (-T_final / (1.0f - alpha)) * bg_dot_dpixel;
+                            dL_dalpha += (-T_final * r1ma) * bg_dot_dpixel;
 
                             const float dL_dG = opa * dL_dalpha;   // alpha cap is straight-through (backward.cu:391)
                             dL_dz += w * dL_ddepth;
@@ -176,7 +179,7 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(
                             if (rho3d <= rho2d) {
                                 const float dLdsx = dL_dG * -G * sx + dL_dz * Tw.x;
                                 const float dLdsy = dL_dG * -G * sy + dL_dz * Tw.y;
-                                const float dsx_pz = dLdsx / p.z, dsy_pz = dLdsy / p.z;
+                                const float dsx_pz = dLdsx * rz, dsy_pz = dLdsy * rz;
                                 const float3 dL_dp = f3(dsx_pz, dsy_pz, -(dsx_pz * sx + dsy_pz * sy));
                                 const float3 dL_dk = cross(l, dL_dp);
                                 const float3 dL_dl = cross(dL_dp, k);

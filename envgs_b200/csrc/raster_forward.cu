@@ -335,7 +335,8 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(
                 float3 l = pyf * Tw - Tv;
                 float3 p = cross(k, l);
                 if (p.z != 0.0f) {
-                    float sx = p.x / p.z, sy = p.y / p.z;
+                    const float rz = 1.0f / p.z;                 // one IEEE reciprocal instead of two divisions (<= 1 ulp apart)
+                    float sx = p.x * rz, sy = p.y * rz;
                     float rho3d = sx * sx + sy * sy;
                     float dx = r2.y - pxf, dy = r2.z - pyf;
                     float rho2d = FILTER_INV_SQUARE * (dx * dx + dy * dy);

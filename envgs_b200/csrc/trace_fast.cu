@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(TF_THREADS) traverse_kernel(const FastParams p
     int node = STACK_EMPTY;
     bool have_ray = false, exhausted = false, overflow = false;
     size_t ray = 0;
-    float3 o = f3(0, 0, 0), d = f3(0, 0, 1), inv = f3(0, 0, 0);
+    float3 o = f3(0, 0, 0), d = f3(0, 0, 1), inv = f3(0, 0, 0), oi = f3(0, 0, 0);
     int cnt = 0, sp = 0, nleaf = 0;
     unsigned int st_nodes = 0, st_prims = 0;
 
@@ -141,6 +141,7 @@ __global__ void __launch_bounds__(TF_THREADS) traverse_kernel(const FastParams p
                     ray = (size_t)row * W + col;
                     o = ld3(p.a.ray_o, (int)ray); d = ld3(p.a.ray_d, (int)ray);
                     inv = f3(safe_inv_f(d.x), safe_inv_f(d.y), safe_inv_f(d.z));
+                    oi = o * inv;
                     cnt = 0; sp = 0; nleaf = 0; overflow = false; st_nodes = 0; st_prims = 0;
                     have_ray = true;
                     node = isfinite(d.x + d.y + d.z + o.x + o.y + o.z) ? 0 : STACK_EMPTY;
@@ -158,31 +159,40 @@ __global__ void __launch_bounds__(TF_THREADS) traverse_kernel(const FastParams p
             const unsigned int am = __ballot_sync(0xffffffffu, act);
             if (am == 0u) break;
             if (can_refill && __popc(am) < p.refill_threshold) break;   // let idle groups fetch new rays (Aila & Laine 2009)
-            bool hit_leaf = false, hit_int = false;
-            int link = 0;
+            bool hit = false;
+            int link = 0, leafmask = 0;
             if (act) {
                 const Bvh4Slot* __restrict__ sl = &nodes4[node].s[sub];
                 const float4 A = __ldg(&sl->a), B = __ldg(&sl->b);
                 link = __float_as_int(B.z);
-                st_nodes++;
-                const float ax = (A.x - o.x) * inv.x, bx = (A.w - o.x) * inv.x;
-                const float ay = (A.y - o.y) * inv.y, by = (B.x - o.y) * inv.y;
-                const float az = (A.z - o.z) * inv.z, bz = (B.y - o.z) * inv.z;
+                leafmask = __float_as_int(B.w);
+                if (p.stats) st_nodes++;
+                const float ax = fmaf(A.x, inv.x, -oi.x), bx = fmaf(A.w, inv.x, -oi.x);
+                const float ay = fmaf(A.y, inv.y, -oi.y), by = fmaf(B.x, inv.y, -oi.y);
+                const float az = fmaf(A.z, inv.z, -oi.z), bz = fmaf(B.y, inv.z, -oi.z);
                 const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
-                const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) * 1.0000004f;
-                const bool hit = (tn <= tf) && (tf > 0.0f);
-                hit_leaf = hit && link < 0;
-                hit_int = hit && link >= 0;
+                const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) * 1.0000008f;
+                hit = (tn <= tf) && (tf > 0.0f);
             }
-            const unsigned int m_leaf = (__ballot_sync(0xffffffffu, hit_leaf) >> gshift) & 0xFu;
-            const unsigned int m_int = (__ballot_sync(0xffffffffu, hit_int) >> gshift) & 0xFu;
-            if (hit_leaf) gleaf[nleaf + __popc(m_leaf & lower)] = ~link;
-            if (hit_int) gstack[sp + __popc(m_int & lower)] = link;
+            // one vote per visit: the node's leaf mask (same in its four slots) splits the hit mask
+            const unsigned int m_hit = (__ballot_sync(0xffffffffu, hit) >> gshift) & 0xFu;
+            const unsigned int m_leaf = m_hit & (unsigned int)leafmask;
+            const unsigned int m_int = m_hit & ~(unsigned int)leafmask;
+            const unsigned int rest = m_int & (m_int - 1u);                      // all but the first hit internal child
+            const int first = __ffs(m_int) - 1;
+            const bool is_leaf = (leafmask >> sub) & 1;
+            // first hit internal child goes straight to the next visit (no stack round trip), the others are pushed
+            const int next = __shfl_sync(0xffffffffu, link, gshift + (first < 0 ? 0 : first));
+            if (hit) {
+                if (is_leaf) gleaf[nleaf + __popc(m_leaf & lower)] = ~link;
+                else if (sub != first) gstack[sp + __popc(rest & lower)] = link;
+            }
             __syncwarp();
             if (act) {
                 nleaf += __popc(m_leaf);
-                sp += __popc(m_int);
-                if (sp == 0) node = STACK_EMPTY;
+                sp += __popc(rest);
+                if (m_int) node = next;
+                else if (sp == 0) node = STACK_EMPTY;
                 else { sp--; node = gstack[sp]; }
             }
             __syncwarp();
@@ -485,8 +495,11 @@ __device__ __forceinline__ float3 sh_basis_grad(int k, float3 d) {
 }
 
 constexpr int GR_STRIDE = 20;   // floats per staged hit-gradient record
+#ifndef SHADE_BWD_MIN_BLOCKS
+#define SHADE_BWD_MIN_BLOCKS 2
+#endif
 
-__global__ void __launch_bounds__(256) shade_bwd_kernel(const FastParams p, int R) {
+__global__ void __launch_bounds__(256, SHADE_BWD_MIN_BLOCKS) shade_bwd_kernel(const FastParams p, int R) {
     // per-hit gradient records staged in shared memory so the 61 atomics of a contributing hit are issued by the whole
     // half-warp (15 small components in one instruction, 48 SH components in three) instead of one lane after another
     __shared__ float s_rec[SH_RAYS_PER_BLOCK * 16 * GR_STRIDE];
