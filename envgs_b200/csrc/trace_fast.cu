@@ -36,23 +36,28 @@ struct FastParams {
     int* counts;                  // [R] number of hits, -1 = overflow (handled by the fallback kernel)
     unsigned int* overflow_count; // [1]
     int* overflow_list;           // [R]
+    unsigned int* class_count;    // [4] rays with 0 / 1-4 / 5-8 / 9-15 hits
+    int* class_list;              // [4][R]
+    int R;
     unsigned int* work_counter;
     unsigned long long* stats;
     int n_items, tiles_x;
     int refill_threshold;         // leave an inner traversal loop when fewer lanes than this are still in it
-    int debug_flags;              // development only: 1 = skip SH atomics, 2 = skip small atomics (timing experiments)
 };
 
 size_t trace_cache_bytes(int H, int W) {
     size_t R = (size_t)H * W;
-    return R * (TF_MAXHITS * sizeof(float2) + 4 + 4) + 1024;
+    return R * (TF_MAXHITS * sizeof(float2) + 4 + 4 + 16) + 1024;
 }
 static void carve_cache(char* base, int H, int W, FastParams& p) {
     size_t R = (size_t)H * W;
+    p.R = (int)R;
     p.hits = reinterpret_cast<float2*>(base);
     p.counts = reinterpret_cast<int*>(base + R * TF_MAXHITS * sizeof(float2));
     p.overflow_list = p.counts + R;
-    p.overflow_count = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(p.overflow_list + R) + 256);
+    p.class_list = p.overflow_list + R;
+    p.overflow_count = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(p.class_list + 4 * R) + 256);
+    p.class_count = p.overflow_count + 4;
 }
 
 __device__ __forceinline__ float safe_inv_f(float d) { return 1.0f / (fabsf(d) > 1e-30f ? d : copysignf(1e-30f, d)); }
@@ -107,14 +112,17 @@ __global__ void __launch_bounds__(TF_THREADS) traverse_kernel(const FastParams p
     while (true) {
         // ---- retire finished rays, refill idle groups (all 32 lanes are converged here) ----
         const bool idle = (node == STACK_EMPTY) && nleaf == 0;
-        if (idle && have_ray) {
-            if (sub == 0) {
+        {
+            const bool retire = idle && have_ray;
+            int cls = -1;   // 0: no hit, 1: 1-4 hits, 2: 5-8, 3: 9-15 (lanes per ray 4 / 8 / 16 in the shading kernels)
+            if (retire && sub == 0) {
                 if (overflow) {
                     p.counts[ray] = -1;
                     const unsigned int k = atomicAdd(p.overflow_count, 1u);
                     p.overflow_list[k] = (int)ray;
                 } else {
                     p.counts[ray] = cnt;
+                    cls = cnt == 0 ? 0 : (cnt <= 4 ? 1 : (cnt <= 8 ? 2 : 3));
                 }
                 if (p.stats) {
                     atomicAdd(&p.stats[0], 1ull); atomicAdd(&p.stats[1], (unsigned long long)st_nodes);
@@ -122,7 +130,20 @@ __global__ void __launch_bounds__(TF_THREADS) traverse_kernel(const FastParams p
                     atomicAdd(&p.stats[4], 1ull);
                 }
             }
-            have_ray = false;
+            if (__any_sync(0xffffffffu, cls >= 0)) {   // warp-aggregated append to the per-class ray lists
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const unsigned int m = __ballot_sync(0xffffffffu, cls == c);
+                    if (m) {
+                        const int leader = __ffs(m) - 1;
+                        unsigned int base = 0;
+                        if (lane == leader) base = atomicAdd(&p.class_count[c], (unsigned int)__popc(m));
+                        base = __shfl_sync(0xffffffffu, base, leader);
+                        if (cls == c) p.class_list[(size_t)c * p.R + base + __popc(m & ((1u << lane) - 1u))] = (int)ray;
+                    }
+                }
+            }
+            if (retire) have_ray = false;
         }
         const bool gwant = idle && !exhausted;
         const unsigned int want = __ballot_sync(0xffffffffu, gwant && sub == 0);
@@ -178,21 +199,16 @@ __global__ void __launch_bounds__(TF_THREADS) traverse_kernel(const FastParams p
             const unsigned int m_hit = (__ballot_sync(0xffffffffu, hit) >> gshift) & 0xFu;
             const unsigned int m_leaf = m_hit & (unsigned int)leafmask;
             const unsigned int m_int = m_hit & ~(unsigned int)leafmask;
-            const unsigned int rest = m_int & (m_int - 1u);                      // all but the first hit internal child
-            const int first = __ffs(m_int) - 1;
             const bool is_leaf = (leafmask >> sub) & 1;
-            // first hit internal child goes straight to the next visit (no stack round trip), the others are pushed
-            const int next = __shfl_sync(0xffffffffu, link, gshift + (first < 0 ? 0 : first));
             if (hit) {
                 if (is_leaf) gleaf[nleaf + __popc(m_leaf & lower)] = ~link;
-                else if (sub != first) gstack[sp + __popc(rest & lower)] = link;
+                else gstack[sp + __popc(m_int & lower)] = link;
             }
             __syncwarp();
             if (act) {
                 nleaf += __popc(m_leaf);
-                sp += __popc(rest);
-                if (m_int) node = next;
-                else if (sp == 0) node = STACK_EMPTY;
+                sp += __popc(m_int);
+                if (sp == 0) node = STACK_EMPTY;
                 else { sp--; node = gstack[sp]; }
             }
             __syncwarp();
@@ -241,47 +257,70 @@ __global__ void __launch_bounds__(TF_THREADS) traverse_kernel(const FastParams p
 }
 
 // ------------------------------------------------------------------------------------------------------
-// hit-parallel shading helpers (16 lanes per ray)
+// hit-parallel shading (L = 4, 8 or 16 lanes per ray, chosen from the ray's hit count)
 // ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float seg_scan_mul(float v, int h) {   // inclusive product over the half-warp
+// A ray's hits are evaluated one per lane.  With a fixed 16 lanes per ray only ~30 % of the lanes carried a hit (mean
+// 4.9 hits per ray, 30 % of the rays hit nothing), so traverse_kernel sorts the rays into classes by hit count and the
+// shading kernels are instantiated for 4, 8 and 16 lanes per ray; rays without hits are written by a trivial kernel.
+template <int L>
+__device__ __forceinline__ float seg_scan_mul(float v, int h) {   // inclusive product over the L lanes of a ray
 #pragma unroll
-    for (int o = 1; o < 16; o <<= 1) {
-        float u = __shfl_up_sync(0xffffffffu, v, o, 16);
+    for (int o = 1; o < L; o <<= 1) {
+        float u = __shfl_up_sync(0xffffffffu, v, o, L);
         if (h >= o) v *= u;
     }
     return v;
 }
-__device__ __forceinline__ float seg_scan_add(float v, int h) {   // inclusive sum over the half-warp
+template <int L>
+__device__ __forceinline__ float seg_scan_add(float v, int h) {   // inclusive sum over the L lanes of a ray
 #pragma unroll
-    for (int o = 1; o < 16; o <<= 1) {
-        float u = __shfl_up_sync(0xffffffffu, v, o, 16);
+    for (int o = 1; o < L; o <<= 1) {
+        float u = __shfl_up_sync(0xffffffffu, v, o, L);
         if (h >= o) v += u;
     }
     return v;
 }
-// transpose-reduce inside a half-warp: lane h ends up with the sum over the 16 lanes of v[h]
-__device__ __forceinline__ float half_transpose_reduce(float (&v)[16], int h) {
+// Transpose-reduce of 16 per-lane values across the L lanes of a ray: afterwards lane h holds, in v[0 .. 16/L), the sums of
+// the components reduce_base<L>(h) + j.  (L = 16: lane h holds component h.)
+template <int L>
+__device__ __forceinline__ void reduce16(float (&v)[16], int h) {
+    int len = 16;
 #pragma unroll
-    for (int s = 8; s >= 1; s >>= 1) {
+    for (int s = L / 2; s >= 1; s >>= 1) {
+        len >>= 1;
         const bool up = (h & s) != 0;
 #pragma unroll
-        for (int i = 0; i < s; i++) {
-            const float send = up ? v[i] : v[i + s];
-            const float keep = up ? v[i + s] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s, 16);
+        for (int i = 0; i < 8; i++) {
+            if (i < len) {
+                const float send = up ? v[i] : v[i + len];
+                const float keep = up ? v[i + len] : v[i];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s, L);
+            }
         }
     }
-    return v[0];
+}
+template <int L>
+__device__ __forceinline__ int reduce_base(int h) { return h * (16 / L); }
+// NOTE: with stages s = L/2 ... 1 halving the vector each time, lane bit s selects the upper half of the current
+// vector, so the surviving block of lane h starts at sum_s (h & s ? len_s : 0) = h * 16 / L.
+
+// all-lanes sum over the L lanes of a ray
+template <int L>
+__device__ __forceinline__ float seg_sum(float v) {
+#pragma unroll
+    for (int o = L / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, L);
+    return v;
 }
 
-// ascending bitonic sort of (t, id) across the 16 lanes of a half-warp; empty slots carry t = +inf
-__device__ __forceinline__ void half_bitonic_sort(float& t, int& id, int h) {
+// ascending bitonic sort of (t, id) across the L lanes of a ray; empty slots carry t = +inf
+template <int L>
+__device__ __forceinline__ void seg_bitonic_sort(float& t, int& id, int h) {
 #pragma unroll
-    for (int k = 2; k <= 16; k <<= 1) {
+    for (int k = 2; k <= L; k <<= 1) {
 #pragma unroll
         for (int j = k >> 1; j > 0; j >>= 1) {
-            const float ot = __shfl_xor_sync(0xffffffffu, t, j, 16);
-            const int oi = __shfl_xor_sync(0xffffffffu, id, j, 16);
+            const float ot = __shfl_xor_sync(0xffffffffu, t, j, L);
+            const int oi = __shfl_xor_sync(0xffffffffu, id, j, L);
             const bool asc = (h & k) == 0;
             const bool lower = (h & j) == 0;
             const bool mine_first = (t < ot) || (t == ot && id < oi);
@@ -304,9 +343,10 @@ struct HitEval {
     int gidx;
 };
 
-// Evaluate this lane's hit and run the transmittance scan.  Returns T_final (same for the 16 lanes).
+// Evaluate this lane's hit and run the transmittance scan.  Returns T_final (same for the L lanes of the ray).
 // When `dL_drgb` is given (backward), shU[k] = w * sum_c sh[k][c] * dL/drgb_c (unclamped channels): the per-hit part of
 // dL/d(direction) through the SH colour, formed while the coefficients are in registers.
+template <int L>
 __device__ __forceinline__ float eval_and_scan(const envgs_trace_args& a, bool valid, float tmx, int gidx, float3 ray_o, float3 ray_d,
                                                const float* __restrict__ basis, int nbasis, bool sh_vec4, float3 campos, int h,
                                                HitEval& e, const float* dL_drgb = nullptr, float* shU = nullptr) {
@@ -345,25 +385,27 @@ __device__ __forceinline__ float eval_and_scan(const envgs_trace_args& a, bool v
         if (e.alpha < 1.0f / 255.0f) cand = false;
     }
     const float one_m = cand ? 1.0f - e.alpha : 1.0f;
-    const float T_incl = seg_scan_mul(one_m, h);
-    float T_excl = __shfl_up_sync(0xffffffffu, T_incl, 1, 16);
+    const float T_incl = seg_scan_mul<L>(one_m, h);
+    float T_excl = __shfl_up_sync(0xffffffffu, T_incl, 1, L);
     if (h == 0) T_excl = 1.0f;
     // termination: the first candidate whose T_next drops below 1e-4 and everything behind it are dropped (forward.cu:370-372)
-    const unsigned int half_shift = (threadIdx.x & 16);
-    const unsigned int stop_mask = (__ballot_sync(0xffffffffu, cand && (T_incl < 0.0001f)) >> half_shift) & 0xffffu;
-    const int stop = stop_mask ? (__ffs(stop_mask) - 1) : 16;
+    const unsigned int seg_shift = (threadIdx.x & 31) & ~(L - 1);
+    const unsigned int seg_mask = L == 32 ? 0xffffffffu : ((1u << L) - 1u);
+    const unsigned int stop_mask = (__ballot_sync(0xffffffffu, cand && (T_incl < 0.0001f)) >> seg_shift) & seg_mask;
+    const int stop = stop_mask ? (__ffs(stop_mask) - 1) : L;
     e.contrib = cand && h < stop;
     e.T_prev = T_excl;
     e.w = e.contrib ? e.alpha * T_excl : 0.0f;
     // final transmittance = product over contributors = inclusive product at the last lane before `stop`
     const int last = stop - 1;
-    float T_final = __shfl_sync(0xffffffffu, T_incl, last < 0 ? 0 : last, 16);
+    float T_final = __shfl_sync(0xffffffffu, T_incl, last < 0 ? 0 : last, L);
     if (last < 0) T_final = 1.0f;
 
     if (e.contrib) {   // colour and auxiliaries only where they are used
         if (a.colors_precomp == nullptr) {
             const float* sh = a.shs + (size_t)gidx * a.sh_coeffs * 3;
             float3 res = f3(0, 0, 0);
+            float gr = 0.0f, gg = 0.0f, gb = 0.0f;
             if (sh_vec4) {
                 const float4* s4 = reinterpret_cast<const float4*>(sh);
                 float tmp[48];
@@ -375,30 +417,23 @@ __device__ __forceinline__ float eval_and_scan(const envgs_trace_args& a, bool v
 #pragma unroll
                 for (int k = 0; k < 16; k++)
                     if (k < nbasis) res += basis[k] * f3(tmp[3 * k], tmp[3 * k + 1], tmp[3 * k + 2]);
-            } else {
-                for (int k = 0; k < nbasis; k++) res += basis[k] * f3(sh[3 * k], sh[3 * k + 1], sh[3 * k + 2]);
-            }
-            res.x += 0.5f; res.y += 0.5f; res.z += 0.5f;
-            e.clamped[0] = res.x < 0; e.clamped[1] = res.y < 0; e.clamped[2] = res.z < 0;
-            e.c = f3(fmaxf(res.x, 0.0f), fmaxf(res.y, 0.0f), fmaxf(res.z, 0.0f));
-            if (shU != nullptr) {
-                const float gr = e.clamped[0] ? 0.0f : dL_drgb[0] * e.w, gg = e.clamped[1] ? 0.0f : dL_drgb[1] * e.w,
-                            gb = e.clamped[2] ? 0.0f : dL_drgb[2] * e.w;
-                if (sh_vec4) {
-                    const float4* s4 = reinterpret_cast<const float4*>(sh);
-                    float tmp[48];
-#pragma unroll
-                    for (int q = 0; q < 12; q++) {
-                        if (q * 4 < nbasis * 3) { float4 v = __ldg(&s4[q]); tmp[4 * q] = v.x; tmp[4 * q + 1] = v.y; tmp[4 * q + 2] = v.z; tmp[4 * q + 3] = v.w; }
-                        else { tmp[4 * q] = tmp[4 * q + 1] = tmp[4 * q + 2] = tmp[4 * q + 3] = 0.0f; }
-                    }
+                res.x += 0.5f; res.y += 0.5f; res.z += 0.5f;
+                if (shU != nullptr) {
+                    gr = res.x < 0 ? 0.0f : dL_drgb[0] * e.w; gg = res.y < 0 ? 0.0f : dL_drgb[1] * e.w; gb = res.z < 0 ? 0.0f : dL_drgb[2] * e.w;
 #pragma unroll
                     for (int k = 0; k < 16; k++) shU[k] = k < nbasis ? tmp[3 * k] * gr + tmp[3 * k + 1] * gg + tmp[3 * k + 2] * gb : 0.0f;
-                } else {
+                }
+            } else {
+                for (int k = 0; k < nbasis; k++) res += basis[k] * f3(sh[3 * k], sh[3 * k + 1], sh[3 * k + 2]);
+                res.x += 0.5f; res.y += 0.5f; res.z += 0.5f;
+                if (shU != nullptr) {
+                    gr = res.x < 0 ? 0.0f : dL_drgb[0] * e.w; gg = res.y < 0 ? 0.0f : dL_drgb[1] * e.w; gb = res.z < 0 ? 0.0f : dL_drgb[2] * e.w;
 #pragma unroll
                     for (int k = 0; k < 16; k++) shU[k] = k < nbasis ? sh[3 * k] * gr + sh[3 * k + 1] * gg + sh[3 * k + 2] * gb : 0.0f;
                 }
             }
+            e.clamped[0] = res.x < 0; e.clamped[1] = res.y < 0; e.clamped[2] = res.z < 0;
+            e.c = f3(fmaxf(res.x, 0.0f), fmaxf(res.y, 0.0f), fmaxf(res.z, 0.0f));
         } else {
             e.c = ld3(a.colors_precomp, gidx);
         }
@@ -410,63 +445,97 @@ __device__ __forceinline__ float eval_and_scan(const envgs_trace_args& a, bool v
     return T_final;
 }
 
-constexpr int SH_RAYS_PER_BLOCK = 16;   // 256 threads
-
-__global__ void __launch_bounds__(256) shade_fwd_kernel(const FastParams p, int R) {
+// rays without any hit: background colour, everything else zero (forward.cu:444-449 with an empty loop)
+__global__ void __launch_bounds__(256) shade_empty_kernel(const FastParams p) {
+    const unsigned int n = p.class_count[0];
     const envgs_trace_args& a = p.a;
-    const int h = threadIdx.x & 15;
-    const long long ray_ll = (long long)blockIdx.x * SH_RAYS_PER_BLOCK + (threadIdx.x >> 4);
-    const bool ray_ok = ray_ll < R;
-    const size_t ray = ray_ok ? (size_t)ray_ll : 0;
-    const int cnt = ray_ok ? p.counts[ray] : -1;
-    const bool live = cnt >= 0;                 // -1: overflow ray, written by the fallback kernel
+    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const size_t ray = (size_t)p.class_list[k];
+        const float3 o = ld3(a.ray_o, (int)ray), d = ld3(a.ray_d, (int)ray);
+        const float b0 = a.background[0], b1 = a.background[1], b2 = a.background[2];
+        p.o.out_rgb[ray * 3] = b0; p.o.out_rgb[ray * 3 + 1] = b1; p.o.out_rgb[ray * 3 + 2] = b2;
+        p.o.out_dpt[ray] = 0.0f; p.o.out_acc[ray] = 0.0f;
+        p.o.out_norm[ray * 3] = 0.0f; p.o.out_norm[ray * 3 + 1] = 0.0f; p.o.out_norm[ray * 3 + 2] = 0.0f;
+        p.o.out_dist[ray * 3] = 0.0f; p.o.out_dist[ray * 3 + 1] = 0.0f; p.o.out_dist[ray * 3 + 2] = 0.0f;
+        p.o.out_aux[ray * 2] = 0.0f; p.o.out_aux[ray * 2 + 1] = 0.0f;
+        float4* m4 = reinterpret_cast<float4*>(p.o.mid_val + ray * 32);
+        m4[0] = make_float4(o.x, o.y, o.z, d.x);
+        m4[1] = make_float4(d.y, d.z, 0.0f, 0.0f);
+        m4[2] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        m4[3] = make_float4(0.0f, b0, b1, b2);
+        m4[4] = m4[5] = m4[6] = m4[7] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+}
+
+template <int L>
+__global__ void __launch_bounds__(256) shade_fwd_kernel(const FastParams p, int cls) {
+    constexpr int RPW = 32 / L;              // rays per warp
+    constexpr int VPL = 16 / L;              // reduced components per lane
+    const envgs_trace_args& a = p.a;
+    const int lane = threadIdx.x & 31;
+    const int h = lane & (L - 1);
+    const unsigned int n = p.class_count[cls];
+    const int* __restrict__ list = p.class_list + (size_t)cls * p.R;
     const float3 campos = f3(a.campos[0], a.campos[1], a.campos[2]);
     const int nbasis = (a.sh_degree + 1) * (a.sh_degree + 1);
     const bool use_sh = a.colors_precomp == nullptr;
     const bool sh_vec4 = use_sh && ((a.sh_coeffs * 3) % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.shs) & 15) == 0);
+    const unsigned int warps_total = (gridDim.x * blockDim.x) >> 5;
+    const unsigned int n_items = (n + RPW - 1) / RPW;
 
-    const float3 ray_o = ld3(a.ray_o, (int)ray), ray_d = ld3(a.ray_d, (int)ray);
-    float basis[16];
-    if (use_sh) sh_basis(a.sh_degree, normalize3(ray_d), basis);
-    const bool valid = live && h < cnt;
-    float hit_t = TR_DEPTH_INF * 4.0f;
-    int hit_id = 0x7fffffff;
-    if (valid) { const float2 hit = p.hits[ray * TF_MAXHITS + h]; hit_t = hit.x; hit_id = __float_as_int(hit.y); }
-    half_bitonic_sort(hit_t, hit_id, h);       // slots [0,cnt) now hold the hits in ascending distance
-    HitEval e;
-    const float T_final = eval_and_scan(a, valid, hit_t, hit_id, ray_o, ray_d, basis, nbasis, sh_vec4, campos, h, e);
+    for (unsigned int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < n_items; item += warps_total) {
+        const unsigned int li = item * RPW + (lane / L);
+        const bool live = li < n;
+        const size_t ray = live ? (size_t)list[li] : 0;
+        const int cnt = live ? p.counts[ray] : 0;
+        const float3 ray_o = ld3(a.ray_o, (int)ray), ray_d = ld3(a.ray_d, (int)ray);
+        float basis[16];
+        if (use_sh) sh_basis(a.sh_degree, normalize3(ray_d), basis);
+        const bool valid = live && h < cnt;
+        float hit_t = TR_DEPTH_INF * 4.0f;
+        int hit_id = 0x7fffffff;
+        if (valid) { const float2 hit = p.hits[ray * TF_MAXHITS + h]; hit_t = hit.x; hit_id = __float_as_int(hit.y); }
+        seg_bitonic_sort<L>(hit_t, hit_id, h);       // slots [0,cnt) now hold the hits in ascending distance
+        HitEval e;
+        const float T_final = eval_and_scan<L>(a, valid, hit_t, hit_id, ray_o, ray_d, basis, nbasis, sh_vec4, campos, h, e);
 
-    // distortion bookkeeping needs exclusive prefix sums of w*m and w*m^2 (forward.cu:405-409)
-    const float m = FAR_N / (FAR_N - NEAR_N) * (1.0f - NEAR_N / e.cmd);
-    const float wm = e.w * m, wmm = e.w * m * m;
-    const float M1_ex = seg_scan_add(wm, h) - wm, M2_ex = seg_scan_add(wmm, h) - wmm;
-    float v[16];
-    v[0] = e.w * (m * m * (1.0f - e.T_prev) + M2_ex - 2.0f * m * M1_ex);
-    v[1] = wm; v[2] = wmm; v[3] = 0.0f; v[4] = 0.0f; v[5] = 0.0f;
-    v[6] = e.w * e.cmd; v[7] = 0.0f;
-    v[8] = e.w * e.normal.x; v[9] = e.w * e.normal.y; v[10] = e.w * e.normal.z;
-    v[11] = e.w * e.oth[0]; v[12] = e.w * e.oth[1];
-    v[13] = e.w * e.c.x; v[14] = e.w * e.c.y; v[15] = e.w * e.c.z;
-    const float tot = half_transpose_reduce(v, h);   // lane h: sum of component h (mid_val layout for h >= 6)
+        // distortion bookkeeping needs exclusive prefix sums of w*m and w*m^2 (forward.cu:405-409)
+        const float m = FAR_N / (FAR_N - NEAR_N) * (1.0f - NEAR_N / e.cmd);
+        const float wm = e.w * m, wmm = e.w * m * m;
+        const float M1_ex = seg_scan_add<L>(wm, h) - wm, M2_ex = seg_scan_add<L>(wmm, h) - wmm;
+        float v[16];
+        v[0] = e.w * (m * m * (1.0f - e.T_prev) + M2_ex - 2.0f * m * M1_ex);
+        v[1] = wm; v[2] = wmm; v[3] = 0.0f; v[4] = 0.0f; v[5] = 0.0f;
+        v[6] = e.w * e.cmd; v[7] = 0.0f;
+        v[8] = e.w * e.normal.x; v[9] = e.w * e.normal.y; v[10] = e.w * e.normal.z;
+        v[11] = e.w * e.oth[0]; v[12] = e.w * e.oth[1];
+        v[13] = e.w * e.c.x; v[14] = e.w * e.c.y; v[15] = e.w * e.c.z;
+        reduce16<L>(v, h);   // v[j], j < VPL: ray-wide sum of component reduce_base(h) + j  (components follow the mid_val layout)
 
-    if (live) {
-        if (a.training && e.contrib) atomicAdd(&p.o.a_weights[e.gidx], e.w);
-        // lane h owns mid_val[h] (config.h:18-26): 0-2 ray_o, 3-5 ray_d, 6 D, 7 A, 8-10 N, 11-12 aux, 13-15 rgb (+ T*bg)
-        float mv;
-        if (h < 3) mv = h == 0 ? ray_o.x : (h == 1 ? ray_o.y : ray_o.z);
-        else if (h < 6) mv = h == 3 ? ray_d.x : (h == 4 ? ray_d.y : ray_d.z);
-        else if (h == 7) mv = 1.0f - T_final;
-        else if (h >= 13) mv = tot + T_final * a.background[h - 13];
-        else mv = tot;
-        float* mid = p.o.mid_val + ray * 32;
-        mid[h] = mv;
-        mid[16 + h] = 0.0f;
-        if (h < 3) p.o.out_dist[ray * 3 + h] = tot;                 // dist, M1, M2
-        else if (h == 6) p.o.out_dpt[ray] = mv;
-        else if (h == 7) p.o.out_acc[ray] = mv;
-        else if (h >= 8 && h <= 10) p.o.out_norm[ray * 3 + (h - 8)] = mv;
-        else if (h == 11 || h == 12) p.o.out_aux[ray * 2 + (h - 11)] = mv;
-        else if (h >= 13) p.o.out_rgb[ray * 3 + (h - 13)] = mv;     // max_trace_depth == 0: f_this = s_prod = 1
+        if (live) {
+            if (a.training && e.contrib) atomicAdd(&p.o.a_weights[e.gidx], e.w);
+            float* mid = p.o.mid_val + ray * 32;
+            const int base = reduce_base<L>(h);
+#pragma unroll
+            for (int j = 0; j < VPL; j++) {
+                const int c = base + j;    // mid_val slot (config.h:18-26): 0-2 ray_o, 3-5 ray_d, 6 D, 7 A, 8-10 N, 11-12 aux, 13-15 rgb (+T*bg)
+                const float tot = v[j];
+                float mv;
+                if (c < 3) mv = c == 0 ? ray_o.x : (c == 1 ? ray_o.y : ray_o.z);
+                else if (c < 6) mv = c == 3 ? ray_d.x : (c == 4 ? ray_d.y : ray_d.z);
+                else if (c == 7) mv = 1.0f - T_final;
+                else if (c >= 13) mv = tot + T_final * a.background[c - 13];
+                else mv = tot;
+                mid[c] = mv;
+                mid[16 + c] = 0.0f;
+                if (c < 3) p.o.out_dist[ray * 3 + c] = tot;                 // dist, M1, M2
+                else if (c == 6) p.o.out_dpt[ray] = mv;
+                else if (c == 7) p.o.out_acc[ray] = mv;
+                else if (c >= 8 && c <= 10) p.o.out_norm[ray * 3 + (c - 8)] = mv;
+                else if (c == 11 || c == 12) p.o.out_aux[ray * 2 + (c - 11)] = mv;
+                else if (c >= 13) p.o.out_rgb[ray * 3 + (c - 13)] = mv;     // max_trace_depth == 0: f_this = s_prod = 1
+            }
+        }
     }
 }
 
@@ -495,194 +564,213 @@ __device__ __forceinline__ float3 sh_basis_grad(int k, float3 d) {
 }
 
 constexpr int GR_STRIDE = 20;   // floats per staged hit-gradient record
-#ifndef SHADE_BWD_MIN_BLOCKS
-#define SHADE_BWD_MIN_BLOCKS 2
-#endif
 
-__global__ void __launch_bounds__(256, SHADE_BWD_MIN_BLOCKS) shade_bwd_kernel(const FastParams p, int R) {
-    // per-hit gradient records staged in shared memory so the 61 atomics of a contributing hit are issued by the whole
-    // half-warp (15 small components in one instruction, 48 SH components in three) instead of one lane after another
-    __shared__ float s_rec[SH_RAYS_PER_BLOCK * 16 * GR_STRIDE];
-    __shared__ float s_basis[SH_RAYS_PER_BLOCK * 16];
+template <int L>
+__global__ void __launch_bounds__(256, 2) shade_bwd_kernel(const FastParams p, int cls) {
+    // per-hit gradient records staged in shared memory so the 61 atomics of a contributing hit are issued by all lanes of
+    // the ray instead of one lane after another
+    constexpr int RPW = 32 / L;
+    constexpr int VPL = 16 / L;
+    __shared__ float s_rec[256 * GR_STRIDE];             // one record per thread (= per hit slot)
+    __shared__ float s_basis[(256 / L) * 16];
     const envgs_trace_args& a = p.a;
     const envgs_trace_grads& g = p.g;
-    const int h = threadIdx.x & 15;
-    const long long ray_ll = (long long)blockIdx.x * SH_RAYS_PER_BLOCK + (threadIdx.x >> 4);
-    const bool ray_ok = ray_ll < R;
-    const size_t ray = ray_ok ? (size_t)ray_ll : 0;
-    const int cnt = ray_ok ? p.counts[ray] : -1;
+    const int lane = threadIdx.x & 31;
+    const int h = lane & (L - 1);
+    const int ray_slot = threadIdx.x / L;                 // ray index within the block
+    const unsigned int n = p.class_count[cls];
+    const int* __restrict__ list = p.class_list + (size_t)cls * p.R;
     const float3 campos = f3(a.campos[0], a.campos[1], a.campos[2]);
     const int nbasis = (a.sh_degree + 1) * (a.sh_degree + 1);
     const bool use_sh = a.colors_precomp == nullptr;
     const bool sh_vec4 = use_sh && ((a.sh_coeffs * 3) % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.shs) & 15) == 0);
+    const bool has_oth = a.others_precomp != nullptr;
+    const unsigned int warps_total = (gridDim.x * blockDim.x) >> 5;
+    const unsigned int n_items = (n + RPW - 1) / RPW;
+    const unsigned int seg_shift = lane & ~(L - 1);
+    const unsigned int seg_mask = (1u << L) - 1u;
 
-    // saved forward state of the (only) segment
-    const float* mid = g.mid_val + ray * 32;
-    const float3 ray_o = f3(mid[MID_RAYO], mid[MID_RAYO + 1], mid[MID_RAYO + 2]);
-    const float3 ray_d = f3(mid[MID_RAYD], mid[MID_RAYD + 1], mid[MID_RAYD + 2]);
-    // backward.cu:952-957 with i = 0: s_prev = 1
-    const bool live = cnt >= 0 && !(length3(ray_d) == 0.0f || 1.0f <= a.specular_threshold);
-    const float seg_rgb[3] = {mid[MID_RGB], mid[MID_RGB + 1], mid[MID_RGB + 2]};
-    const float seg_dpt = mid[MID_DPT], seg_acc = mid[MID_ACC];
-    const float3 seg_norm = f3(mid[MID_NORM], mid[MID_NORM + 1], mid[MID_NORM + 2]);
-    const float seg_aux[2] = {mid[MID_AUX], mid[MID_AUX + 1]};
-    const float dL_drgb[3] = {g.dL_drgb[ray * 3], g.dL_drgb[ray * 3 + 1], g.dL_drgb[ray * 3 + 2]};
-    const float dL_ddpt = g.dL_ddpt[ray];
-    const float3 dL_dnorm = ld3(g.dL_dnorm, (int)ray);
-    const float dL_daux[2] = {g.dL_daux[ray * 2], g.dL_daux[ray * 2 + 1]};
-    const float T_final_saved = 1.0f - seg_acc;
+    for (unsigned int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < n_items; item += warps_total) {
+        const unsigned int li = item * RPW + (lane / L);
+        const bool in_list = li < n;
+        const size_t ray = in_list ? (size_t)list[li] : 0;
+        const int cnt = in_list ? p.counts[ray] : 0;
+        // saved forward state of the (only) segment
+        const float* mid = g.mid_val + ray * 32;
+        const float3 ray_o = f3(mid[MID_RAYO], mid[MID_RAYO + 1], mid[MID_RAYO + 2]);
+        const float3 ray_d = f3(mid[MID_RAYD], mid[MID_RAYD + 1], mid[MID_RAYD + 2]);
+        // backward.cu:952-957 with i = 0: s_prev = 1
+        const bool live = in_list && !(length3(ray_d) == 0.0f || 1.0f <= a.specular_threshold);
+        const float seg_rgb[3] = {mid[MID_RGB], mid[MID_RGB + 1], mid[MID_RGB + 2]};
+        const float seg_dpt = mid[MID_DPT], seg_acc = mid[MID_ACC];
+        const float3 seg_norm = f3(mid[MID_NORM], mid[MID_NORM + 1], mid[MID_NORM + 2]);
+        const float seg_aux[2] = {mid[MID_AUX], mid[MID_AUX + 1]};
+        const float dL_drgb[3] = {g.dL_drgb[ray * 3], g.dL_drgb[ray * 3 + 1], g.dL_drgb[ray * 3 + 2]};
+        const float dL_ddpt = g.dL_ddpt[ray];
+        const float3 dL_dnorm = ld3(g.dL_dnorm, (int)ray);
+        const float dL_daux[2] = {g.dL_daux[ray * 2], g.dL_daux[ray * 2 + 1]};
+        const float T_final_saved = 1.0f - seg_acc;
 
-    float basis[16];
-    const float3 dirn = normalize3(ray_d);
-    if (use_sh) sh_basis(a.sh_degree, dirn, basis);
-    const bool valid = live && h < cnt;
-    float hit_t = TR_DEPTH_INF * 4.0f;
-    int hit_id = 0x7fffffff;
-    if (valid) { const float2 hit = p.hits[ray * TF_MAXHITS + h]; hit_t = hit.x; hit_id = __float_as_int(hit.y); }
-    half_bitonic_sort(hit_t, hit_id, h);
-    HitEval e;
-    float shU[16];
+        float basis[16];
+        const float3 dirn = normalize3(ray_d);
+        if (use_sh) sh_basis(a.sh_degree, dirn, basis);
+        const bool valid = live && h < cnt;
+        float hit_t = TR_DEPTH_INF * 4.0f;
+        int hit_id = 0x7fffffff;
+        if (valid) { const float2 hit = p.hits[ray * TF_MAXHITS + h]; hit_t = hit.x; hit_id = __float_as_int(hit.y); }
+        seg_bitonic_sort<L>(hit_t, hit_id, h);
+        HitEval e;
+        float shU[16];
 #pragma unroll
-    for (int k = 0; k < 16; k++) shU[k] = 0.0f;
-    eval_and_scan(a, valid, hit_t, hit_id, ray_o, ray_d, basis, nbasis, sh_vec4, campos, h, e, dL_drgb, use_sh ? shU : nullptr);
+        for (int k = 0; k < 16; k++) shU[k] = 0.0f;
+        eval_and_scan<L>(a, valid, hit_t, hit_id, ray_o, ray_d, basis, nbasis, sh_vec4, campos, h, e, dL_drgb, use_sh ? shU : nullptr);
 
-    // inclusive prefix sums the reference keeps in C, O, D, N while walking front to back
-    const float Cx = seg_scan_add(e.w * e.c.x, h), Cy = seg_scan_add(e.w * e.c.y, h), Cz = seg_scan_add(e.w * e.c.z, h);
-    const float O0 = seg_scan_add(e.w * e.oth[0], h), O1 = seg_scan_add(e.w * e.oth[1], h);
-    const float Dp = seg_scan_add(e.w * e.cmd, h);
-    const float Nx = seg_scan_add(e.w * e.normal.x, h), Ny = seg_scan_add(e.w * e.normal.y, h), Nz = seg_scan_add(e.w * e.normal.z, h);
+        // inclusive prefix sums the reference keeps in C, O, D, N while walking front to back
+        const float Cx = seg_scan_add<L>(e.w * e.c.x, h), Cy = seg_scan_add<L>(e.w * e.c.y, h), Cz = seg_scan_add<L>(e.w * e.c.z, h);
+        const float O0 = seg_scan_add<L>(e.w * e.oth[0], h), O1 = seg_scan_add<L>(e.w * e.oth[1], h);
+        const float Dp = seg_scan_add<L>(e.w * e.cmd, h);
+        const float Nx = seg_scan_add<L>(e.w * e.normal.x, h), Ny = seg_scan_add<L>(e.w * e.normal.y, h), Nz = seg_scan_add<L>(e.w * e.normal.z, h);
 
-    float3 g_ray_o = f3(0, 0, 0), g_ray_d = f3(0, 0, 0);
-    if (e.contrib) {
-        const int gidx = e.gidx;
-        const float alpha = e.alpha, T_prev = e.T_prev, w = e.w, G = e.G, cmd = e.cmd;
-        const float cc[3] = {e.c.x, e.c.y, e.c.z}, Cc[3] = {Cx, Cy, Cz}, O[2] = {O0, O1};
-        float dL_dalpha = 0.0f;
-        float dL_dcolor[3];
+        float3 g_ray_o = f3(0, 0, 0), g_ray_d = f3(0, 0, 0);
+        if (e.contrib) {
+            const int gidx = e.gidx;
+            const float alpha = e.alpha, T_prev = e.T_prev, w = e.w, G = e.G, cmd = e.cmd;
+            const float r1ma = 1.0f / (1.0f - alpha);
+            const float cc[3] = {e.c.x, e.c.y, e.c.z}, Cc[3] = {Cx, Cy, Cz}, O[2] = {O0, O1};
+            float dL_dalpha = 0.0f;
+            float dL_dcolor[3];
 #pragma unroll
-        for (int ch = 0; ch < 3; ch++) {
-            dL_dcolor[ch] = dL_drgb[ch] * w;
-            dL_dalpha += dL_drgb[ch] * (T_prev * cc[ch] - (seg_rgb[ch] - Cc[ch]) / (1.0f - alpha));
-            dL_dalpha += dL_drgb[ch] * a.background[ch] * (-T_final_saved / (1.0f - alpha));
-        }
-        float dL_doth[2] = {0.0f, 0.0f};
-        if (a.others_precomp != nullptr) {
-#pragma unroll
-            for (int ch = 0; ch < 2; ch++) {
-                dL_doth[ch] = dL_daux[ch] * w;
-                dL_dalpha += dL_daux[ch] * (T_prev * e.oth[ch] - (seg_aux[ch] - O[ch]) / (1.0f - alpha));
+            for (int ch = 0; ch < 3; ch++) {
+                dL_dcolor[ch] = dL_drgb[ch] * w;
+                dL_dalpha += dL_drgb[ch] * (T_prev * cc[ch] - (seg_rgb[ch] - Cc[ch]) * r1ma);
+                dL_dalpha += dL_drgb[ch] * a.background[ch] * (-T_final_saved * r1ma);
             }
-        }
-        const float dL_dD = dL_ddpt * w;
-        dL_dalpha += dL_ddpt * (T_prev * cmd - (seg_dpt - Dp) / (1.0f - alpha));
-        const float3 dL_dN = dL_dnorm * w;
-        dL_dalpha += sum3(dL_dnorm * (T_prev * e.normal - (seg_norm - f3(Nx, Ny, Nz)) / (1.0f - alpha)));
-        const float dL_dG = dL_dalpha * e.opac;
-        const float dL_dopac = dL_dalpha * G;   // straight-through cap (backward.cu:801-806)
+            float dL_doth[2] = {0.0f, 0.0f};
+            if (has_oth) {
+#pragma unroll
+                for (int ch = 0; ch < 2; ch++) {
+                    dL_doth[ch] = dL_daux[ch] * w;
+                    dL_dalpha += dL_daux[ch] * (T_prev * e.oth[ch] - (seg_aux[ch] - O[ch]) * r1ma);
+                }
+            }
+            const float dL_dD = dL_ddpt * w;
+            dL_dalpha += dL_ddpt * (T_prev * cmd - (seg_dpt - Dp) * r1ma);
+            const float3 dL_dN = dL_dnorm * w;
+            dL_dalpha += sum3(dL_dnorm * (T_prev * e.normal - (seg_norm - f3(Nx, Ny, Nz)) * r1ma));
+            const float dL_dG = dL_dalpha * e.opac;
+            const float dL_dopac = dL_dalpha * G;   // straight-through cap (backward.cu:801-806)
 
-        // compute_transmat_uv_backward (backward.cu:233-335), plane form t = m.(mu-o)/(m.d), m = t_u x t_v
-        const float2 dL_duv = make_float2(dL_dG * -G * e.uv.x, dL_dG * -G * e.uv.y);
-        const float3 xm = e.xyz - e.mu;
-        float3 dR0 = (dL_duv.x / e.scale.x) * xm;
-        float3 dR1 = (dL_duv.y / e.scale.y) * xm;
-        const float3 dR2 = e.nsign * dL_dN;
-        const float2 dL_dscale = make_float2(dL_dG * (G * e.uv.x * e.uv.x / e.scale.x), dL_dG * (G * e.uv.y * e.uv.y / e.scale.y));
-        float3 dL_dmean = dL_dG * (G * ((e.uv.x / e.scale.x) * e.tu + (e.uv.y / e.scale.y) * e.tv));
-        const float3 dL_dxyz = (dL_duv.x / e.scale.x) * e.tu + (dL_duv.y / e.scale.y) * e.tv;
-        const float dL_dd = dL_dD + dot(dL_dxyz, ray_d);
-        const float3 mvec = cross(e.tu, e.tv);
-        const float qd = dot(mvec, ray_d);
-        const float3 cvec = e.mu - ray_o;
-        const float pn = dot(mvec, cvec);
-        const float3 dt_dm = (cvec - (pn / qd) * ray_d) / qd;
-        dR0 += dL_dd * cross(e.tv, dt_dm);
-        dR1 += dL_dd * cross(dt_dm, e.tu);
-        dL_dmean += dL_dd * (mvec / qd);
-        g_ray_o = dL_dxyz + dL_dd * (-(mvec / qd));
-        g_ray_d = dL_dxyz * cmd + dL_dd * (-pn / (qd * qd)) * mvec;
-        Rot3 gR; gR.c0 = dR0; gR.c1 = dR1; gR.c2 = dR2;
-        const float4 dL_drot = quat_to_rot_vjp(e.rot, gR);
+            // compute_transmat_uv_backward (backward.cu:233-335), plane form t = m.(mu-o)/(m.d), m = t_u x t_v
+            const float isx = 1.0f / e.scale.x, isy = 1.0f / e.scale.y;
+            const float2 dL_duv = make_float2(dL_dG * -G * e.uv.x, dL_dG * -G * e.uv.y);
+            const float3 xm = e.xyz - e.mu;
+            float3 dR0 = (dL_duv.x * isx) * xm;
+            float3 dR1 = (dL_duv.y * isy) * xm;
+            const float3 dR2 = e.nsign * dL_dN;
+            const float2 dL_dscale = make_float2(dL_dG * (G * e.uv.x * e.uv.x * isx), dL_dG * (G * e.uv.y * e.uv.y * isy));
+            float3 dL_dmean = dL_dG * (G * ((e.uv.x * isx) * e.tu + (e.uv.y * isy) * e.tv));
+            const float3 dL_dxyz = (dL_duv.x * isx) * e.tu + (dL_duv.y * isy) * e.tv;
+            const float dL_dd = dL_dD + dot(dL_dxyz, ray_d);
+            const float3 mvec = cross(e.tu, e.tv);
+            const float iqd = 1.0f / dot(mvec, ray_d);
+            const float3 cvec = e.mu - ray_o;
+            const float pn = dot(mvec, cvec);
+            const float3 dt_dm = (cvec - (pn * iqd) * ray_d) * iqd;
+            dR0 += dL_dd * cross(e.tv, dt_dm);
+            dR1 += dL_dd * cross(dt_dm, e.tu);
+            dL_dmean += (dL_dd * iqd) * mvec;
+            g_ray_o = dL_dxyz - (dL_dd * iqd) * mvec;
+            g_ray_d = dL_dxyz * cmd - (dL_dd * pn * iqd * iqd) * mvec;
+            Rot3 gR; gR.c0 = dR0; gR.c1 = dR1; gR.c2 = dR2;
+            const float4 dL_drot = quat_to_rot_vjp(e.rot, gR);
 
-        float3 dRGB = f3(0, 0, 0);
-        if (use_sh) {
-            dRGB = f3(e.clamped[0] ? 0.0f : dL_dcolor[0], e.clamped[1] ? 0.0f : dL_dcolor[1], e.clamped[2] ? 0.0f : dL_dcolor[2]);
+            float3 dRGB = f3(0, 0, 0);
+            if (use_sh) dRGB = f3(e.clamped[0] ? 0.0f : dL_dcolor[0], e.clamped[1] ? 0.0f : dL_dcolor[1], e.clamped[2] ? 0.0f : dL_dcolor[2]);
+            float* rec = s_rec + threadIdx.x * GR_STRIDE;
+            rec[0] = dL_dscale.x; rec[1] = dL_dscale.y;
+            rec[2] = dL_drot.x; rec[3] = dL_drot.y; rec[4] = dL_drot.z; rec[5] = dL_drot.w;
+            rec[6] = dL_dmean.x; rec[7] = dL_dmean.y; rec[8] = dL_dmean.z;
+            rec[9] = dL_dcolor[0]; rec[10] = dL_dcolor[1]; rec[11] = dL_dcolor[2];
+            rec[12] = dL_dopac; rec[13] = dL_doth[0]; rec[14] = dL_doth[1];
+            rec[15] = dRGB.x; rec[16] = dRGB.y; rec[17] = dRGB.z;
+            rec[18] = __int_as_float(gidx);
         }
-        float* rec = s_rec + ((threadIdx.x >> 4) * 16 + h) * GR_STRIDE;
-        rec[0] = dL_dscale.x; rec[1] = dL_dscale.y;
-        rec[2] = dL_drot.x; rec[3] = dL_drot.y; rec[4] = dL_drot.z; rec[5] = dL_drot.w;
-        rec[6] = dL_dmean.x; rec[7] = dL_dmean.y; rec[8] = dL_dmean.z;
-        rec[9] = dL_dcolor[0]; rec[10] = dL_dcolor[1]; rec[11] = dL_dcolor[2];
-        rec[12] = dL_dopac; rec[13] = dL_doth[0]; rec[14] = dL_doth[1];
-        rec[15] = dRGB.x; rec[16] = dRGB.y; rec[17] = dRGB.z;
-        rec[18] = __int_as_float(gidx);
-    }
-    // ---- cooperative scatter: the half-warp walks its contributing hits; lane q owns component q / SH coefficient q ----
-    {
-        float my_basis = 0.0f;
-        if (use_sh) {
-            float* sb = s_basis + (threadIdx.x >> 4) * 16;
-            if (h == 0) {
+        // ---- cooperative scatter: the ray's lanes walk its contributing hits; lane q takes components q, q+L, ... ----
+        {
+            float* sb = s_basis + ray_slot * 16;
+            if (use_sh && h == 0) {
 #pragma unroll
                 for (int k = 0; k < 16; k++) sb[k] = k < nbasis ? basis[k] : 0.0f;
             }
             __syncwarp();
-            my_basis = sb[h];
-        } else {
-            __syncwarp();
-        }
-        const unsigned int half_shift = (threadIdx.x & 16);
-        unsigned int cm = (__ballot_sync(0xffffffffu, e.contrib) >> half_shift) & 0xffffu;
-        const bool has_oth = a.others_precomp != nullptr;
-        while (__any_sync(0xffffffffu, cm != 0u)) {
-            if (cm != 0u) {
-                const int hit = __ffs(cm) - 1;
-                cm &= cm - 1u;
-                const float* rec = s_rec + ((threadIdx.x >> 4) * 16 + hit) * GR_STRIDE;
-                const size_t gi = (size_t)__float_as_int(rec[18]);
-                if (h < 15) {
-                    const float v = rec[h];
-                    float* dst;
-                    if (h < 2) dst = g.dL_dscales + 2 * gi + h;
-                    else if (h < 6) dst = g.dL_drotations + 4 * gi + (h - 2);
-                    else if (h < 9) dst = g.dL_dmeans3D + 3 * gi + (h - 6);
-                    else if (h < 12) dst = g.dL_dcolors + 3 * gi + (h - 9);
-                    else if (h == 12) dst = g.dL_dopacities + gi;
-                    else dst = has_oth ? g.dL_dothers + 2 * gi + (h - 13) : nullptr;
-                    if (dst != nullptr && !(p.debug_flags & 2)) atomicAdd(dst, v);
-                }
-                if (use_sh && h < nbasis && !(p.debug_flags & 1)) {
-                    float* dsh = g.dL_dshs + gi * a.sh_coeffs * 3 + 3 * h;
-                    atomicAdd(dsh + 0, my_basis * rec[15]);
-                    atomicAdd(dsh + 1, my_basis * rec[16]);
-                    atomicAdd(dsh + 2, my_basis * rec[17]);
+            unsigned int cm = (__ballot_sync(0xffffffffu, e.contrib) >> seg_shift) & seg_mask;
+            while (__any_sync(0xffffffffu, cm != 0u)) {
+                if (cm != 0u) {
+                    const int hit = __ffs(cm) - 1;
+                    cm &= cm - 1u;
+                    const float* rec = s_rec + (ray_slot * L + hit) * GR_STRIDE;
+                    const size_t gi = (size_t)__float_as_int(rec[18]);
+#pragma unroll
+                    for (int q0 = 0; q0 < 16; q0 += L) {
+                        const int q = q0 + h;
+                        if (q < 15) {
+                            float* dst;
+                            if (q < 2) dst = g.dL_dscales + 2 * gi + q;
+                            else if (q < 6) dst = g.dL_drotations + 4 * gi + (q - 2);
+                            else if (q < 9) dst = g.dL_dmeans3D + 3 * gi + (q - 6);
+                            else if (q < 12) dst = g.dL_dcolors + 3 * gi + (q - 9);
+                            else if (q == 12) dst = g.dL_dopacities + gi;
+                            else dst = has_oth ? g.dL_dothers + 2 * gi + (q - 13) : nullptr;
+                            if (dst != nullptr) atomicAdd(dst, rec[q]);
+                        }
+                    }
+                    if (use_sh) {
+#pragma unroll
+                        for (int k0 = 0; k0 < 16; k0 += L) {
+                            const int k = k0 + h;
+                            if (k < nbasis) {
+                                const float bk = sb[k];
+                                float* dsh = g.dL_dshs + gi * a.sh_coeffs * 3 + 3 * k;
+                                atomicAdd(dsh + 0, bk * rec[15]);
+                                atomicAdd(dsh + 1, bk * rec[16]);
+                                atomicAdd(dsh + 2, bk * rec[17]);
+                            }
+                        }
+                    }
                 }
             }
+            __syncwarp();
         }
-    }
-    // per-ray gradients: sum over the 16 hits
-    float v[16];
-    v[0] = g_ray_o.x; v[1] = g_ray_o.y; v[2] = g_ray_o.z; v[3] = g_ray_d.x; v[4] = g_ray_d.y; v[5] = g_ray_d.z;
+        // ---- per-ray gradients: sum over the hits ----
+        float v[16];
+        v[0] = g_ray_o.x; v[1] = g_ray_o.y; v[2] = g_ray_o.z; v[3] = g_ray_d.x; v[4] = g_ray_d.y; v[5] = g_ray_d.z;
 #pragma unroll
-    for (int i = 6; i < 16; i++) v[i] = 0.0f;
-    const float tot = half_transpose_reduce(v, h);
-    // SH direction gradient: lane k gets U_k = sum over hits of shU[k]; dL/ddir = sum_k U_k * grad basis_k(dir)
-    float sx = 0.0f, sy = 0.0f, sz = 0.0f;
-    if (use_sh) {
-        const float Uk = half_transpose_reduce(shU, h);
-        const float3 gb = sh_basis_grad(h < nbasis ? h : 0, dirn);
-        sx = Uk * gb.x; sy = Uk * gb.y; sz = Uk * gb.z;
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) {
-            sx += __shfl_xor_sync(0xffffffffu, sx, o, 16);
-            sy += __shfl_xor_sync(0xffffffffu, sy, o, 16);
-            sz += __shfl_xor_sync(0xffffffffu, sz, o, 16);
-        }
-    }
-    if (ray_ok && cnt >= 0) {   // overflow rays (cnt < 0) are written by the fallback kernel
+        for (int i = 6; i < 16; i++) v[i] = 0.0f;
+        reduce16<L>(v, h);
+        // SH direction gradient: dL/ddir = sum_k U_k * grad basis_k(dir), U_k = sum over hits of shU[k]
         float3 extra = f3(0, 0, 0);
-        if (use_sh && live) extra = dnormvdv(ray_d, f3(sx, sy, sz));   // backward.cu:182-184
-        if (h < 3) g.dL_dray_o[ray * 3 + h] = live ? tot : 0.0f;
-        else if (h < 6) g.dL_dray_d[ray * 3 + (h - 3)] = live ? tot + (h == 3 ? extra.x : (h == 4 ? extra.y : extra.z)) : 0.0f;
+        if (use_sh) {
+            reduce16<L>(shU, h);
+            const int base = reduce_base<L>(h);
+            float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+#pragma unroll
+            for (int j = 0; j < VPL; j++) {
+                const int k = base + j;
+                const float3 gb = sh_basis_grad(k < nbasis ? k : 0, dirn);
+                sx += shU[j] * gb.x; sy += shU[j] * gb.y; sz += shU[j] * gb.z;
+            }
+            sx = seg_sum<L>(sx); sy = seg_sum<L>(sy); sz = seg_sum<L>(sz);
+            if (live) extra = dnormvdv(ray_d, f3(sx, sy, sz));   // backward.cu:182-184
+        }
+        if (in_list) {
+            const int base = reduce_base<L>(h);
+#pragma unroll
+            for (int j = 0; j < VPL; j++) {
+                const int c = base + j;
+                if (c < 3) g.dL_dray_o[ray * 3 + c] = live ? v[j] : 0.0f;
+                else if (c < 6) g.dL_dray_d[ray * 3 + (c - 3)] = live ? v[j] + (c == 3 ? extra.x : (c == 4 ? extra.y : extra.z)) : 0.0f;
+            }
+        }
     }
 }
 
@@ -726,7 +814,7 @@ int trace_forward_fast(Lbvh& bvh, unsigned int* counter, unsigned long long* sta
     else { p.tiles_x = 0; p.n_items = (int)(((long long)a.H * a.W + 31) / 32); }
     const int R = a.H * a.W;
     ENVGS_CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream));
-    ENVGS_CUDA_TRY(cudaMemsetAsync(p.overflow_count, 0, sizeof(unsigned int), stream));
+    ENVGS_CUDA_TRY(cudaMemsetAsync(p.overflow_count, 0, 8 * sizeof(unsigned int), stream));   // overflow + 4 class counters
     int blocks = sm_count * occ;
     int need = (p.n_items * 32 + (TF_THREADS / 4) - 1) / (TF_THREADS / 4);
     if (blocks > need) blocks = need > 0 ? need : 1;
@@ -743,8 +831,15 @@ int trace_forward_fast(Lbvh& bvh, unsigned int* counter, unsigned long long* sta
     ENVGS_CUDA_TRY(cudaEventRecord(side.join, side.stream));
     {
         ENVGS_TIMED("trace_shade_fwd", stream);
-        shade_fwd_kernel<<<(R + SH_RAYS_PER_BLOCK - 1) / SH_RAYS_PER_BLOCK, 256, 0, stream>>>(p, R);
-        ENVGS_LAUNCH_CHECK("trace_shade_fwd", false, stream);
+        const int sblocks = sm_count * 8;
+        shade_empty_kernel<<<sblocks, 256, 0, stream>>>(p);
+        ENVGS_LAUNCH_CHECK("trace_shade_empty", false, stream);
+        shade_fwd_kernel<4><<<sblocks, 256, 0, stream>>>(p, 1);
+        ENVGS_LAUNCH_CHECK("trace_shade_fwd4", false, stream);
+        shade_fwd_kernel<8><<<sblocks, 256, 0, stream>>>(p, 2);
+        ENVGS_LAUNCH_CHECK("trace_shade_fwd8", false, stream);
+        shade_fwd_kernel<16><<<sblocks, 256, 0, stream>>>(p, 3);
+        ENVGS_LAUNCH_CHECK("trace_shade_fwd16", false, stream);
     }
     ENVGS_CUDA_TRY(cudaStreamWaitEvent(stream, side.join, 0));
     return ENVGS_OK;
@@ -756,8 +851,12 @@ int trace_backward_fast(Lbvh& bvh, unsigned int* counter, unsigned long long* st
     memset(&p, 0, sizeof(p));
     p.nodes = bvh.nodes; p.prims = bvh.prims; p.a = a; p.g = g;
     carve_cache((char*)cache, a.H, a.W, p);
-    { const char* e = getenv("ENVGS_DEBUG_FLAGS"); p.debug_flags = e ? atoi(e) : 0; }
-    const int R = a.H * a.W;
+    const size_t R = (size_t)a.H * a.W;
+    int sm_count = 148;
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
+    // rays without hits (class 0) and rays skipped by the kernels keep a zero ray gradient
+    ENVGS_CUDA_TRY(cudaMemsetAsync(g.dL_dray_o, 0, R * 3 * sizeof(float), stream));
+    ENVGS_CUDA_TRY(cudaMemsetAsync(g.dL_dray_d, 0, R * 3 * sizeof(float), stream));
     ENVGS_CUDA_TRY(cudaEventRecord(side.fork, stream));
     ENVGS_CUDA_TRY(cudaStreamWaitEvent(side.stream, side.fork, 0));
     int rc = launch_trace(true, bvh, counter, stats, a, nullptr, &g, p.overflow_list, p.overflow_count, side.stream);
@@ -765,8 +864,13 @@ int trace_backward_fast(Lbvh& bvh, unsigned int* counter, unsigned long long* st
     ENVGS_CUDA_TRY(cudaEventRecord(side.join, side.stream));
     {
         ENVGS_TIMED("trace_shade_bwd", stream);
-        shade_bwd_kernel<<<(R + SH_RAYS_PER_BLOCK - 1) / SH_RAYS_PER_BLOCK, 256, 0, stream>>>(p, R);
-        ENVGS_LAUNCH_CHECK("trace_shade_bwd", false, stream);
+        const int sblocks = sm_count * 2;
+        shade_bwd_kernel<4><<<sblocks, 256, 0, stream>>>(p, 1);
+        ENVGS_LAUNCH_CHECK("trace_shade_bwd4", false, stream);
+        shade_bwd_kernel<8><<<sblocks, 256, 0, stream>>>(p, 2);
+        ENVGS_LAUNCH_CHECK("trace_shade_bwd8", false, stream);
+        shade_bwd_kernel<16><<<sblocks, 256, 0, stream>>>(p, 3);
+        ENVGS_LAUNCH_CHECK("trace_shade_bwd16", false, stream);
     }
     ENVGS_CUDA_TRY(cudaStreamWaitEvent(stream, side.join, 0));
     return ENVGS_OK;
