@@ -134,3 +134,21 @@ def test_full_size_properties(built_lib):
     # surfels nobody hit get no gradient
     untouched = cu["wet"][:, 0] == 0
     assert float(cu["g_means"][untouched].abs().max()) == 0
+
+
+def test_fast_path_equals_general_kernel(built_lib, monkeypatch):
+    """EnvGS' call shape takes the BVH4 + hit-parallel fast path; ENVGS_TRACE_FORCE_MONOLITHIC=1 routes the same call through
+    the general chunk-loop kernel.  Both must agree (they share nothing but the BVH build)."""
+    env = scene.make_env_set(5000, seed=4, s0=0.06)
+    cam = scene.ring_cameras(1, 36, 52, seed=2)[0]
+    ro, rd = Hh.synthetic_rays(36, 52, seed=9)
+    up = _up(36, 52, 60)
+    fast = Hh.run_cuda_trace(env, cam, ro, rd, grads=up)
+    monkeypatch.setenv("ENVGS_TRACE_FORCE_MONOLITHIC", "1")
+    gen = Hh.run_cuda_trace(env, cam, ro, rd, grads=up)
+    monkeypatch.delenv("ENVGS_TRACE_FORCE_MONOLITHIC")
+    for k in ("rgb", "dpt", "acc", "norm", "mid", "dist"):
+        assert Hh.frac_above(fast[k], gen[k], 1e-5 * max(1.0, float(gen[k].abs().max()))) < 1e-4, Hh.image_report(k, fast[k], gen[k], 1e-5)
+    for k in ("g_means", "g_opac", "g_scales", "g_rots", "g_shs", "g_ray_o", "g_ray_d"):
+        assert Hh.rel_l2(fast[k], gen[k]) < 2e-4, f"{k}: {Hh.rel_l2(fast[k], gen[k]):.3e}"
+    assert Hh.rel_l2(fast["wet"].reshape(-1), gen["wet"].reshape(-1)) < 1e-5
