@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libenvgs_b200.so")
+LIB_PATH = os.environ.get("ENVGS_B200_LIB") or os.path.join(_HERE, "libenvgs_b200.so")   # override: kernel A/B experiments only
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
 

@@ -12,8 +12,11 @@ namespace envgs {
 constexpr int BB = 128;          // surfels staged per batch (CTA = 256 threads; keeps static smem < 48 KB for C = 7)
 constexpr int NG_FIX = 15;       // reduced values besides colour: normal(3) opacity(1) dT(9) dmean2D(2)
 
+#ifndef RBWD_MINBLOCKS
+#define RBWD_MINBLOCKS 2
+#endif
 template <int C>
-__global__ void __launch_bounds__(256) render_bwd_kernel(
+__global__ void __launch_bounds__(256, RBWD_MINBLOCKS) render_bwd_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int tiles_x,
     const float* __restrict__ bg, const float4* __restrict__ rec, const short4* __restrict__ pixbox,
     const float* __restrict__ features, const float* __restrict__ final_Ts, const uint32_t* __restrict__ n_contrib,
@@ -100,11 +103,23 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(
         }
         __syncthreads();
 
-        for (int j = 0; j < nb; j++) {
+        // Candidate compaction: 32 staged surfels are box-tested at once (one per lane) against this warp's 8x4 pixel
+        // block and the ballot is walked bit by bit, so a rejected surfel costs no loop iteration at all (63 % of the
+        // (warp, surfel) pairs are rejected; the former one-by-one scan spent 20 % of the kernel's instructions on them).
+        for (int c0 = 0; c0 < nb; c0 += 32) {
+        bool cand = false;
+        {
+            const int jj = c0 + lane;
+            if (jj < nb && (uint32_t)(total - i * BB - jj) <= warp_last) {
+                const short4 bb = s_box[jj];
+                cand = !(bb.x > wx1 || bb.z < wx0 || bb.y > wy1 || bb.w < wy0);
+            }
+        }
+        unsigned int cmask = __ballot_sync(0xffffffffu, cand);
+        while (cmask) {
+            const int j = c0 + __ffs(cmask) - 1;
+            cmask &= cmask - 1;
             const uint32_t pos = (uint32_t)(total - i * BB - j);
-            if (pos > warp_last) continue;                                           // warp-uniform
-            const short4 bb = s_box[j];
-            if (bb.x > wx1 || bb.z < wx0 || bb.y > wy1 || bb.w < wy0) continue;   // warp-uniform
             const float4 r0 = s_r0[j], r1 = s_r1[j], r2 = s_r2[j];
             const float3 Tu = f3(r0.x, r0.y, r0.z), Tv = f3(r0.w, r1.x, r1.y), Tw = f3(r1.z, r1.w, r2.x);
 
@@ -203,6 +218,7 @@ __global__ void __launch_bounds__(256) render_bwd_kernel(
             // warp -> CTA reduction: transpose-reduce (lane q ends up with the warp sum of component q), one shared atomic per lane
             const float tot = warp_transpose_reduce<NG>(g, lane);
             if (lane < NG && tot != 0.0f) atomicAdd(&s_g[j * NG + lane], tot);
+        }
         }
         __syncthreads();
         // flush this batch: thread t owns surfel slot t

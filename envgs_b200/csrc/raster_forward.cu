@@ -322,9 +322,21 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(
 
         const int nb = min(RB, toDo);
         bool warp_done = __all_sync(0xffffffffu, done);
-        for (int j = 0; j < nb && !warp_done; j++) {
-            const short4 bb = s_box[j];
-            if (bb.x > wx1 || bb.z < wx0 || bb.y > wy1 || bb.w < wy0) continue;   // warp-uniform reject
+        // Candidate compaction: 32 staged surfels are box-tested at once (one per lane) against this warp's 8x4 pixel
+        // block and the ballot is walked bit by bit, so a rejected surfel costs no loop iteration at all.
+        for (int c0 = 0; c0 < nb && !warp_done; c0 += 32) {
+        bool cand = false;
+        {
+            const int jj = c0 + lane;
+            if (jj < nb) {
+                const short4 bb = s_box[jj];
+                cand = !(bb.x > wx1 || bb.z < wx0 || bb.y > wy1 || bb.w < wy0);
+            }
+        }
+        unsigned int cmask = __ballot_sync(0xffffffffu, cand);
+        while (cmask && !warp_done) {
+            const int j = c0 + __ffs(cmask) - 1;
+            cmask &= cmask - 1;
             const float4 r0 = s_r0[j], r1 = s_r1[j], r2 = s_r2[j];
             const float3 Tu = f3(r0.x, r0.y, r0.z), Tv = f3(r0.w, r1.x, r1.y), Tw = f3(r1.z, r1.w, r2.x);
             float w = 0.0f;
@@ -377,6 +389,7 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(
                 if (lane == 0) atomicAdd(&s_wacc[j], ws);
             }
             warp_done = __all_sync(0xffffffffu, done);
+        }
         }
         __syncthreads();
         if (tid < nb) {

@@ -1,11 +1,12 @@
 // trace_fast.cu — the tracer's fast path for EnvGS' own call shape (max_trace_depth = 0, start_from_first = false):
 //
-//   traverse_kernel   one ray per lane, persistent warps over 8x4 pixel blocks, "while-while" LBVH traversal
-//                     (inner loop over internal nodes, inner loop over leaves) with the per-lane stack and hit list in
-//                     shared memory.  Finds ALL quad hits of the ray; a ray with more than 15 hits is handed to the
-//                     monolithic kernel of trace.cu (which implements the reference's 16-hit chunk restart exactly).
-//                     Hits are rank-sorted by distance straight into HBM: hits[ray][16] (t, surfel) = one 128-byte line.
-//   shade_fwd_kernel  HIT-parallel: a half-warp (16 lanes) per ray, one hit per lane.  Per-hit evaluation (surfel
+//   traverse_kernel   four lanes per ray on the 4-wide BVH (one child slot per lane), persistent warps with group-level
+//                     refill, two phases per round (node visits with queued leaves, then quad tests four at a time), the
+//                     per-ray stack and leaf queue in shared memory.  Finds ALL quad hits of the ray; a ray with more
+//                     than 15 hits is handed to the general kernel of trace.cu (which implements the reference's 16-hit
+//                     chunk restart exactly).  Hits are appended unsorted to hits[ray][16] (t, surfel) = one 128-byte
+//                     line; rays are binned by hit count into per-class lists for the shading kernels.
+//   shade_fwd_kernel  HIT-parallel: 4, 8 or 16 lanes per ray (by hit count), one hit per lane.  Per-hit evaluation (surfel
 //                     frame, alpha, SH colour) runs in parallel; the front-to-back recurrence T_i = T_{i-1}(1-a_i) is a
 //                     4-step segmented shuffle scan; every accumulated output is one transpose-reduce.
 //   shade_bwd_kernel  same layout; the reference's suffix terms (F - F_i)/(1-a_i) come from inclusive scans.  It re-uses
@@ -87,22 +88,36 @@ __device__ __forceinline__ bool ray_of_index(const FastParams& p, unsigned int k
 // Here lane j of a group loads child slot j (32 B) of the 128-byte node, so a visit costs the group ONE cache line
 // (two wavefronts for 8 rays per instruction), each lane slab-tests one child, and the hit masks are combined with a
 // group-wide ballot.  Reached leaves are queued and quad-tested four at a time (one per lane).
-__global__ void __launch_bounds__(TF_THREADS) traverse_kernel(const FastParams p) {
-    __shared__ int s_stack[(TF_THREADS / 4) * T4_STACK];
-    __shared__ int s_leafq[(TF_THREADS / 4) * T4_LEAFQ];
+// Shared memory is addressed through explicit 32-bit shared-window addresses (st.shared / ld.shared): with ordinary
+// array indexing ptxas re-derived the window base (S2UR CgaCtaId + ULEA) and the group offset (S2R tid) at every access,
+// ~10 % of the inner loop's instructions.  Per group: [0, T4_STACK) traversal stack, [T4_STACK, T4_GROUP) leaf queue.
+constexpr int T4_GROUP = T4_STACK + T4_LEAFQ;
+__device__ __forceinline__ void sts32(unsigned int addr, int v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ int lds32(unsigned int addr) {
+    int v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+
+#ifndef T4_MINBLOCKS
+#define T4_MINBLOCKS 9
+#endif
+template <bool STATS>
+__global__ void __launch_bounds__(TF_THREADS, T4_MINBLOCKS) traverse_kernel(const FastParams p) {
+    __shared__ int s_buf[(TF_THREADS / 4) * T4_GROUP];
     const int lane = threadIdx.x & 31;
     const int sub = lane & 3;
     const int gshift = lane & ~3;
     const unsigned int lower = (1u << sub) - 1u;
-    int* gstack = s_stack + (threadIdx.x >> 2) * T4_STACK;
-    int* gleaf = s_leafq + (threadIdx.x >> 2) * T4_LEAFQ;
+    unsigned int sbase;   // byte address of this group's slice in the shared window, pinned in a register
+    asm volatile("mov.u32 %0, %1;" : "=r"(sbase) : "r"((unsigned int)__cvta_generic_to_shared(s_buf) + (threadIdx.x >> 2) * (T4_GROUP * 4)));
     const int W = p.a.W;
-    const Bvh4Node* __restrict__ nodes4 = p.nodes4;
+    const char* __restrict__ slot0 = reinterpret_cast<const char*>(p.nodes4) + 32 * sub;   // this lane's child slot of node 0
     const QuadPrim* __restrict__ prims = p.prims;
     const unsigned int total = (unsigned int)p.n_items * 32u;
 
     // per-ray state, replicated in the four lanes of the group
-    int node = STACK_EMPTY;
+    int node = STACK_EMPTY, nodeB = STACK_EMPTY;   // the (up to) two nodes of the next round; nodeB is only set when node is
     bool have_ray = false, exhausted = false, overflow = false;
     size_t ray = 0;
     float3 o = f3(0, 0, 0), d = f3(0, 0, 1), inv = f3(0, 0, 0), oi = f3(0, 0, 0);
@@ -124,7 +139,7 @@ __global__ void __launch_bounds__(TF_THREADS) traverse_kernel(const FastParams p
                     p.counts[ray] = cnt;
                     cls = cnt == 0 ? 0 : (cnt <= 4 ? 1 : (cnt <= 8 ? 2 : 3));
                 }
-                if (p.stats) {
+                if (STATS) {
                     atomicAdd(&p.stats[0], 1ull); atomicAdd(&p.stats[1], (unsigned long long)st_nodes);
                     atomicAdd(&p.stats[2], (unsigned long long)st_prims); atomicAdd(&p.stats[3], (unsigned long long)cnt);
                     atomicAdd(&p.stats[4], 1ull);
@@ -166,6 +181,7 @@ __global__ void __launch_bounds__(TF_THREADS) traverse_kernel(const FastParams p
                     cnt = 0; sp = 0; nleaf = 0; overflow = false; st_nodes = 0; st_prims = 0;
                     have_ray = true;
                     node = isfinite(d.x + d.y + d.z + o.x + o.y + o.z) ? 0 : STACK_EMPTY;
+                    nodeB = STACK_EMPTY;
                 }
             }
         }
@@ -175,81 +191,88 @@ __global__ void __launch_bounds__(TF_THREADS) traverse_kernel(const FastParams p
         // The warp stays converged (full-mask votes, idle groups predicated off): per-group vote masks would split the
         // warp into eight 4-lane fragments that are issued one after the other.
         const bool can_refill = __any_sync(0xffffffffu, idle && !exhausted);
+        // TWO nodes per group per round (the two topmost stack entries): their loads are independent, which doubles the
+        // memory-level parallelism of the pointer chase and amortises the round's votes and loop control.
         while (true) {
-            const bool act = node != STACK_EMPTY && nleaf <= T4_LEAFQ - 4 && sp <= T4_STACK - 4;
+            const bool act = node != STACK_EMPTY && nleaf <= T4_LEAFQ - 8 && sp <= T4_STACK - 8;
             const unsigned int am = __ballot_sync(0xffffffffu, act);
             if (am == 0u) break;
             if (can_refill && __popc(am) < p.refill_threshold) break;   // let idle groups fetch new rays (Aila & Laine 2009)
-            bool hit = false;
-            int link = 0, leafmask = 0;
-            if (act) {
-                const Bvh4Slot* __restrict__ sl = &nodes4[node].s[sub];
-                const float4 A = __ldg(&sl->a), B = __ldg(&sl->b);
-                link = __float_as_int(B.z);
-                leafmask = __float_as_int(B.w);
-                if (p.stats) st_nodes++;
-                const float ax = fmaf(A.x, inv.x, -oi.x), bx = fmaf(A.w, inv.x, -oi.x);
-                const float ay = fmaf(A.y, inv.y, -oi.y), by = fmaf(B.x, inv.y, -oi.y);
-                const float az = fmaf(A.z, inv.z, -oi.z), bz = fmaf(B.y, inv.z, -oi.z);
+            const bool actB = act && nodeB != STACK_EMPTY;
+            const unsigned int ndA = act ? (unsigned int)node : 0u, ndB = actB ? (unsigned int)nodeB : 0u;
+            const Bvh4Slot* __restrict__ slA = reinterpret_cast<const Bvh4Slot*>(slot0 + ((size_t)ndA << 7));
+            const Bvh4Slot* __restrict__ slB = reinterpret_cast<const Bvh4Slot*>(slot0 + ((size_t)ndB << 7));
+            const float4 A0 = __ldg(&slA->a), A1 = __ldg(&slA->b), B0 = __ldg(&slB->a), B1 = __ldg(&slB->b);
+            if (STATS) st_nodes += (act ? 1u : 0u) + (actB ? 1u : 0u);
+            bool hitA, hitB;
+            {
+                const float ax = fmaf(A0.x, inv.x, -oi.x), bx = fmaf(A0.w, inv.x, -oi.x);
+                const float ay = fmaf(A0.y, inv.y, -oi.y), by = fmaf(A1.x, inv.y, -oi.y);
+                const float az = fmaf(A0.z, inv.z, -oi.z), bz = fmaf(A1.y, inv.z, -oi.z);
                 const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
                 const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) * 1.0000008f;
-                hit = (tn <= tf) && (tf > 0.0f);
+                hitA = act && (tn <= tf) && (tf > 0.0f);
             }
-            // one vote per visit: the node's leaf mask (same in its four slots) splits the hit mask
-            const unsigned int m_hit = (__ballot_sync(0xffffffffu, hit) >> gshift) & 0xFu;
-            const unsigned int m_leaf = m_hit & (unsigned int)leafmask;
-            const unsigned int m_int = m_hit & ~(unsigned int)leafmask;
-            const bool is_leaf = (leafmask >> sub) & 1;
-            if (hit) {
-                if (is_leaf) gleaf[nleaf + __popc(m_leaf & lower)] = ~link;
-                else gstack[sp + __popc(m_int & lower)] = link;
+            {
+                const float ax = fmaf(B0.x, inv.x, -oi.x), bx = fmaf(B0.w, inv.x, -oi.x);
+                const float ay = fmaf(B0.y, inv.y, -oi.y), by = fmaf(B1.x, inv.y, -oi.y);
+                const float az = fmaf(B0.z, inv.z, -oi.z), bz = fmaf(B1.y, inv.z, -oi.z);
+                const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+                const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) * 1.0000008f;
+                hitB = actB && (tn <= tf) && (tf > 0.0f);
             }
+            const unsigned int lmA = (unsigned int)__float_as_int(A1.w), lmB = (unsigned int)__float_as_int(B1.w);
+            const unsigned int mA = (__ballot_sync(0xffffffffu, hitA) >> gshift) & 0xFu;
+            const unsigned int mB = (__ballot_sync(0xffffffffu, hitB) >> gshift) & 0xFu;
+            const unsigned int mlA = mA & lmA, miA = mA & ~lmA, mlB = mB & lmB, miB = mB & ~lmB;
+            const int nlA = __popc(mlA), niA = __popc(miA);
+            const bool leafA = (lmA >> sub) & 1u, leafB = (lmB >> sub) & 1u;
+            const int atA = (leafA ? T4_STACK + nleaf : sp) + __popc((leafA ? mlA : miA) & lower);
+            const int atB = (leafB ? T4_STACK + nleaf + nlA : sp + niA) + __popc((leafB ? mlB : miB) & lower);
+            const unsigned int adA = sbase + 4u * (unsigned int)atA, adB = sbase + 4u * (unsigned int)atB;
+            if (hitA) sts32(adA, __float_as_int(A1.z));
+            if (hitB) sts32(adB, __float_as_int(B1.z));
             __syncwarp();
-            if (act) {
-                nleaf += __popc(m_leaf);
-                sp += __popc(m_int);
-                if (sp == 0) node = STACK_EMPTY;
-                else { sp--; node = gstack[sp]; }
-            }
+            nleaf += nlA + __popc(mlB);          // all masks are 0 for idle groups
+            sp += niA + __popc(miB);
+            const bool popA = act && sp > 0, popB = act && sp > 1;
+            const int tA = lds32(sbase + 4u * (unsigned int)max(sp - 1, 0));
+            const int tB = lds32(sbase + 4u * (unsigned int)max(sp - 2, 0));
+            node = popA ? tA : (act ? STACK_EMPTY : node);
+            nodeB = popB ? tB : (act ? STACK_EMPTY : nodeB);
+            sp -= (popA ? 1 : 0) + (popB ? 1 : 0);
             __syncwarp();
         }
-        if (sp > T4_STACK - 4 && node != STACK_EMPTY && nleaf <= T4_LEAFQ - 4) {
+        if (sp > T4_STACK - 8 && node != STACK_EMPTY && nleaf <= T4_LEAFQ - 8) {
             // stack capacity reached (pathologically deep tree): hand the ray to the general kernel
-            overflow = true; node = STACK_EMPTY; sp = 0; nleaf = 0;
+            overflow = true; node = STACK_EMPTY; nodeB = STACK_EMPTY; sp = 0; nleaf = 0;
         }
         // ---- phase 2: queued quads, four at a time (warp-uniform trip count) ----
         for (int i0 = 0; __any_sync(0xffffffffu, i0 < nleaf); i0 += 4) {
+            // branch-free quad test: lanes without a queued leaf test surfel 0 with the result masked off; a ray parallel
+            // to the plane gives t = inf/nan, which fails the range test exactly like the reference's q != 0 guard
             const int i = i0 + sub;
-            bool hit = false;
-            float t = 0.0f;
-            int sid = 0;
-            if (i < nleaf) {
-                sid = gleaf[i];
-                st_prims++;
-                const float4 pn = __ldg(&prims[sid].n);
-                const float4 pv = __ldg(&prims[sid].v1);
-                const float3 n = f3(pn.x, pn.y, pn.z);
-                const float q = dot(n, d);
-                if (q != 0.0f) {
-                    const float3 v1 = f3(pv.x, pv.y, pv.z);
-                    t = dot(n, v1 - o) / q;
-                    if (t > 0.0f && t < TR_DEPTH_INF) {
-                        const float4 pu = __ldg(&prims[sid].eu);
-                        const float4 pw = __ldg(&prims[sid].ev);
-                        const float3 r = (o + t * d) - v1;
-                        const float a = dot(r, f3(pu.x, pu.y, pu.z)) * pv.w;
-                        const float b = dot(r, f3(pw.x, pw.y, pw.z)) * pu.w;
-                        hit = pw.w != 0.0f && a >= 0.0f && a <= 1.0f && b >= 0.0f && b <= 1.0f;
-                    }
-                }
-            }
+            const bool valid = i < nleaf;
+            const int qv = lds32(sbase + 4u * (unsigned int)(T4_STACK + min(i, T4_LEAFQ - 1)));
+            const int sid = valid ? ~qv : 0;
+            if (STATS) st_prims += valid ? 1u : 0u;
+            const QuadPrim* __restrict__ pr = prims + sid;
+            const float4 pn = __ldg(&pr->n), pv = __ldg(&pr->v1), pu = __ldg(&pr->eu), pw = __ldg(&pr->ev);
+            const float3 n = f3(pn.x, pn.y, pn.z), v1 = f3(pv.x, pv.y, pv.z);
+            const float q = dot(n, d);
+            const float t = dot(n, v1 - o) / q;
+            const float3 r = (o + t * d) - v1;
+            const float a = dot(r, f3(pu.x, pu.y, pu.z)) * pv.w;
+            const float b = dot(r, f3(pw.x, pw.y, pw.z)) * pu.w;
+            const bool hit = valid && q != 0.0f && t > 0.0f && t < TR_DEPTH_INF && pw.w != 0.0f && a >= 0.0f && a <= 1.0f &&
+                             b >= 0.0f && b <= 1.0f;
             const unsigned int hm = (__ballot_sync(0xffffffffu, hit) >> gshift) & 0xFu;
             if (hit) {
                 const int slot = cnt + __popc(hm & lower);
                 if (slot < TF_MAXHITS) p.hits[ray * TF_MAXHITS + slot] = make_float2(t, __int_as_float(sid));
             }
             cnt += __popc(hm);
-            if (cnt >= TF_MAXHITS && !overflow) { overflow = true; sp = 0; node = STACK_EMPTY; nleaf = 0; }   // full chunk: general kernel
+            if (cnt >= TF_MAXHITS && !overflow) { overflow = true; sp = 0; node = STACK_EMPTY; nodeB = STACK_EMPTY; nleaf = 0; }   // full chunk: general kernel
         }
         nleaf = 0;
         __syncwarp();
@@ -797,7 +820,7 @@ int trace_forward_fast(Lbvh& bvh, unsigned int* counter, unsigned long long* sta
         int dev = 0;
         ENVGS_CUDA_TRY(cudaGetDevice(&dev));
         ENVGS_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-        ENVGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, traverse_kernel, TF_THREADS, 0));
+        ENVGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, traverse_kernel<false>, TF_THREADS, 0));
         if (occ < 1) occ = 1;
     }
     FastParams p;
@@ -820,7 +843,8 @@ int trace_forward_fast(Lbvh& bvh, unsigned int* counter, unsigned long long* sta
     if (blocks > need) blocks = need > 0 ? need : 1;
     {
         ENVGS_TIMED("trace_traverse", stream);
-        traverse_kernel<<<blocks, TF_THREADS, 0, stream>>>(p);
+        if (stats) traverse_kernel<true><<<blocks, TF_THREADS, 0, stream>>>(p);
+        else traverse_kernel<false><<<blocks, TF_THREADS, 0, stream>>>(p);
         ENVGS_LAUNCH_CHECK("trace_traverse", false, stream);
     }
     // rays whose first chunk was full: the reference's multi-chunk loop, run by the general kernel on the device-side list
