@@ -41,6 +41,10 @@ def _f32c(t: torch.Tensor | None, device) -> torch.Tensor | None:
     return t.detach().to(torch.float32).contiguous()
 
 
+_ALLOC_QUANTUM = 32 << 20
+_ALLOC_HWM: dict = {}   # (device, buffer role) -> largest rounded request so far
+
+
 class _Scratch:
     """Allocator callbacks handed to the C ABI: three torch byte tensors owned by the autograd context."""
 
@@ -53,8 +57,19 @@ class _Scratch:
 
     def _make(self, name):
         def alloc(_user, nbytes):
+            # The binning buffer scales with the number of (tile, surfel) instances, which changes from view to view.  A
+            # varying request size makes torch's caching allocator split and re-carve its big blocks step after step
+            # (measured: reserved memory creeping from 3 to 10 GB and a 30-110 ms cudaMalloc stall every few views).  Sizes
+            # are therefore rounded up to a coarse quantum and never shrink below the largest request seen on this device:
+            # after the first few views every step issues the identical allocation sequence and the allocator is quiet.
+            n = max(int(nbytes), 1)
+            if n > (4 << 20):
+                n = (n + _ALLOC_QUANTUM - 1) // _ALLOC_QUANTUM * _ALLOC_QUANTUM
+                key = (str(self.device), name)
+                n = max(n, _ALLOC_HWM.get(key, 0))
+                _ALLOC_HWM[key] = n
             try:
-                t = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=self.device)
+                t = torch.empty(n, dtype=torch.uint8, device=self.device)
             except Exception:  # surfaced by the library as ENVGS_ERR_ALLOC
                 return None
             self.bufs[name] = t
