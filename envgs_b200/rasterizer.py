@@ -80,6 +80,12 @@ class _Scratch:
         t = self.bufs.get(name)
         return t if t is not None else torch.empty(0, dtype=torch.uint8, device=self.device)
 
+    def close(self):
+        """Break the self -> callback thunk -> closure -> self cycle: otherwise the ~300 MB of scratch this object holds
+        is only released when Python's cyclic GC happens to run, and the caching allocator keeps growing (3 -> 10 GB)."""
+        self.bufs = {}
+        self.cbs = {}
+
 
 def _make_args(C_channels, settings, bg, means3D, sh, colors, opacities, scales, rotations, cov, viewmatrix,
                projmatrix, campos):
@@ -179,8 +185,9 @@ def make_module(C_channels: int):
             ctx.raster_settings = s
             ctx.num_rendered = num_rendered
             ctx.bg = bg
-            ctx.save_for_backward(col, m3, sc, rot, cov, radii, shc, opa, scratch.get("geom"), scratch.get("binning"),
-                                  scratch.get("img"))
+            geom_buf, binning_buf, img_buf = scratch.get("geom"), scratch.get("binning"), scratch.get("img")
+            scratch.close()
+            ctx.save_for_backward(col, m3, sc, rot, cov, radii, shc, opa, geom_buf, binning_buf, img_buf)
             ctx.mark_non_differentiable(radii)
             return color, radii, others, weight
 

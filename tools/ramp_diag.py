@@ -40,6 +40,8 @@ if mode == "nosync":       # the bench pattern: no host sync between steps; per-
     for s in range(70):
         if s < 12 or s % 5 == 0:
             print(f"step {s:3d} gpu-interval {evs[s].elapsed_time(evs[s + 1]):7.2f} ms  cpu {cpu[s]:7.2f} ms")
+    import gc
+    a0 = torch.cuda.memory_allocated() >> 20; n = gc.collect(); print("gc.collect() ->", n, "objects; allocated", a0, "->", torch.cuda.memory_allocated() >> 20, "MB")
     st = torch.cuda.memory_stats(); print("cudaMallocs", st["num_device_alloc"], "reserved", torch.cuda.memory_reserved() >> 20, "allocated", torch.cuda.memory_allocated() >> 20, "peak", torch.cuda.max_memory_allocated() >> 20)
     segs = sorted(torch.cuda.memory_snapshot(), key=lambda x: -x["total_size"])[:12]
     for sg in segs: print("  segment", sg["total_size"] >> 20, "MB active", sg["active_size"] >> 20, "blocks", len(sg["blocks"]))
