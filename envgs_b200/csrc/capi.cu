@@ -238,7 +238,7 @@ int envgs_glue_blend_loss_backward(const envgs_glue_camera* cam, const float* im
 }
 
 static int check_features(int32_t P, int32_t D, int32_t M, int32_t E) {
-    if (P < 0 || E < 0 || D < 0 || D > 3 || (D + 1) * (D + 1) > M) { set_error("bad sh_features arguments P=%d D=%d M=%d E=%d", P, D, M, E); return ENVGS_ERR_INVALID; }
+    if (P < 0 || E < 0 || D < 0 || D > 3 || (D + 1) * (D + 1) > M || M > 16) { set_error("bad sh_features arguments P=%d D=%d M=%d E=%d", P, D, M, E); return ENVGS_ERR_INVALID; }
     return ENVGS_OK;
 }
 int envgs_sh_features_forward(int32_t P, int32_t D, int32_t M, int32_t E, const float* means3D, const float* shs, const float* extra,

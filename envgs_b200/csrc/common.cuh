@@ -191,24 +191,48 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// Warp "transpose-reduce": every lane holds NV (<= 32) partial values v[0..NV-1] (v[i] = 0 for i >= NV); after the
-// call lane l holds the warp-wide sum of v[l].  31 shuffles in 5 dependent stages instead of 5*NV for NV separate
-// butterfly sums — the reduction step of render_bwd (one atomic per lane afterwards).
-template <int NV>
-__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane) {
+// Warp "split-reduce": every lane holds N (<= 32) partial values v[0..N-1]; afterwards each of the N components' warp-wide
+// sum sits in exactly one lane (warp_split_component<N>(lane) tells which, -1 = none).  Recursive halving over the lane
+// bits 16, 8, 4, 2, 1: at each stage the lower half of the lanes keeps the first ceil(n/2) values and the upper half the
+// rest, so a stage costs ceil(n/2) shuffles and the whole reduction N/2 + N/4 + ... (21 shuffles for N = 20) instead of
+// the 5*N of N separate butterfly sums or the 31 of a power-of-two transpose.  The reduction step of render_bwd.
+template <int N, int H>
+struct WarpSplitReduce {
+    static __device__ __forceinline__ float run(float (&v)[32], int lane) {
+        constexpr int NL = (N + 1) / 2;
+        const bool up = (lane & H) != 0;
 #pragma unroll
-    for (int i = NV; i < 32; i++) v[i] = 0.0f;
+        for (int i = 0; i < NL; i++) {
+            const float hi = (NL + i < N) ? v[NL + i] : 0.0f;
+            const float send = up ? v[i] : hi;
+            const float keep = up ? hi : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, H);
+        }
+        return WarpSplitReduce<NL, H / 2>::run(v, lane);
+    }
+};
+template <int N>
+struct WarpSplitReduce<N, 0> {
+    static __device__ __forceinline__ float run(float (&v)[32], int) { return v[0]; }
+};
+template <int N>
+__device__ __forceinline__ float warp_split_reduce(float (&v)[32], int lane) {
+    static_assert(N >= 1 && N <= 32, "at most one component per lane");
+    return WarpSplitReduce<N, 16>::run(v, lane);
+}
+// which component's sum lane `lane` holds after warp_split_reduce<N> (-1: none)
+template <int N>
+__device__ __forceinline__ int warp_split_component(int lane) {
+    // n: values every lane of the current group carries (the upper half is zero-padded to ceil(n/2)); real: how many of them
+    // are components rather than padding
+    int lo = 0, n = N, real = N;
 #pragma unroll
     for (int h = 16; h >= 1; h >>= 1) {
-        const bool up = (lane & h) != 0;
-#pragma unroll
-        for (int i = 0; i < h; i++) {
-            const float send = up ? v[i] : v[i + h];
-            const float keep = up ? v[i + h] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
-        }
+        const int nl = (n + 1) / 2;
+        if (lane & h) { lo += nl; real -= nl; } else { real = real < nl ? real : nl; }
+        n = nl;
     }
-    return v[0];
+    return real >= 1 ? lo : -1;
 }
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

@@ -32,18 +32,65 @@ __device__ __forceinline__ float3 sh_basis_grad_k(int k, float3 d) {
     }
 }
 
+// Both kernels: one surfel per thread, but the (P, M, 3) coefficient rows of a warp's 32 consecutive surfels are ONE
+// contiguous 32*M*12-byte block, so the warp moves it with coalesced 16-byte accesses through a padded shared-memory tile
+// (row stride M*3+1 words: conflict-free per-thread row walks).  A thread-per-row walk straight to global memory touched 32
+// different 128-byte lines per instruction and ran at 1.2 TB/s.
+constexpr int SHF_THREADS = 128;
+constexpr int SHF_MAXROW = 48;            // M * 3 floats per surfel (M <= 16)
+
+__device__ __forceinline__ void shf_tile_load(const float* __restrict__ shs, int P, int row_floats, int warp_first, int lane, float* tile) {
+    const size_t base = (size_t)warp_first * row_floats;
+    const int n_rows = min(32, P - warp_first);
+    const int total = n_rows * row_floats;
+    if ((row_floats & 3) == 0 && (reinterpret_cast<uintptr_t>(shs) & 15) == 0) {
+        const float4* src = reinterpret_cast<const float4*>(shs + base);
+        for (int q = lane; q < total / 4; q += 32) {
+            const float4 v = __ldg(src + q);
+            const int f = 4 * q, r = f / row_floats, c = f - r * row_floats;   // a float4 never straddles rows (row_floats % 4 == 0)
+            float* t = tile + r * (row_floats + 1) + c;
+            t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+        }
+    } else {
+        for (int f = lane; f < total; f += 32) { const int r = f / row_floats, c = f - r * row_floats; tile[r * (row_floats + 1) + c] = shs[base + f]; }
+    }
+}
+__device__ __forceinline__ void shf_tile_store(float* __restrict__ dst, int P, int row_floats, int warp_first, int lane, const float* tile) {
+    const size_t base = (size_t)warp_first * row_floats;
+    const int n_rows = min(32, P - warp_first);
+    const int total = n_rows * row_floats;
+    if ((row_floats & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        float4* out = reinterpret_cast<float4*>(dst + base);
+        for (int q = lane; q < total / 4; q += 32) {
+            const int f = 4 * q, r = f / row_floats, c = f - r * row_floats;
+            const float* t = tile + r * (row_floats + 1) + c;
+            out[q] = make_float4(t[0], t[1], t[2], t[3]);
+        }
+    } else {
+        for (int f = lane; f < total; f += 32) { const int r = f / row_floats, c = f - r * row_floats; dst[base + f] = tile[r * (row_floats + 1) + c]; }
+    }
+}
+
 // out (P, 3 + E): rgb | extra (E columns copied from `extra`, e.g. specular, roughness)
-__global__ void __launch_bounds__(256) sh_features_fwd_kernel(int P, int D, int M, int E, const float* __restrict__ means,
-                                                              const float* __restrict__ shs, const float* __restrict__ extra,
-                                                              const float* __restrict__ campos, float* __restrict__ out) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(SHF_THREADS) sh_features_fwd_kernel(int P, int D, int M, int E, const float* __restrict__ means,
+                                                                      const float* __restrict__ shs, const float* __restrict__ extra,
+                                                                      const float* __restrict__ campos, float* __restrict__ out) {
+    __shared__ float s_tile[(SHF_THREADS / 32) * 32 * (SHF_MAXROW + 1)];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int warp_first = blockIdx.x * SHF_THREADS + warp * 32;
+    if (warp_first >= P) return;
+    const int row = M * 3;
+    float* tile = s_tile + warp * 32 * (SHF_MAXROW + 1);
+    shf_tile_load(shs, P, row, warp_first, lane, tile);
+    __syncwarp();
+    const int i = warp_first + lane;
     if (i >= P) return;
     float3 dir = ld3(means, i) - f3(campos[0], campos[1], campos[2]);
     dir = dir / fmaxf(length3(dir), 1e-12f);   // F.normalize's eps
     float b[16];
     sh_basis(D, dir, b);
     const int nb = (D + 1) * (D + 1);
-    const float* sh = shs + (size_t)i * M * 3;
+    const float* sh = tile + lane * (row + 1);
     float3 res = f3(0, 0, 0);
     for (int k = 0; k < nb; k++) res += b[k] * f3(sh[3 * k], sh[3 * k + 1], sh[3 * k + 2]);
     float* o = out + (size_t)i * (3 + E);
@@ -51,44 +98,54 @@ __global__ void __launch_bounds__(256) sh_features_fwd_kernel(int P, int D, int 
     for (int e = 0; e < E; e++) o[3 + e] = extra[(size_t)i * E + e];
 }
 
-__global__ void __launch_bounds__(256) sh_features_bwd_kernel(int P, int D, int M, int E, const float* __restrict__ means,
-                                                              const float* __restrict__ shs, const float* __restrict__ campos,
-                                                              const float* __restrict__ dL_dout, float* __restrict__ dL_dmeans,
-                                                              float* __restrict__ dL_dshs, float* __restrict__ dL_dextra) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P) return;
-    const float3 dir_orig = ld3(means, i) - f3(campos[0], campos[1], campos[2]);
-    const float len = fmaxf(length3(dir_orig), 1e-12f);
-    const float3 dir = dir_orig / len;
-    float b[16];
-    sh_basis(D, dir, b);
-    const int nb = (D + 1) * (D + 1);
-    const float* sh = shs + (size_t)i * M * 3;
-    float3 res = f3(0, 0, 0);
-    for (int k = 0; k < nb; k++) res += b[k] * f3(sh[3 * k], sh[3 * k + 1], sh[3 * k + 2]);
-    const float* g = dL_dout + (size_t)i * (3 + E);
-    // clamp_min(x + 0.5, 0): gradient passes where the pre-clamp value is >= 0
-    const float3 dRGB = f3(res.x + 0.5f >= 0.0f ? g[0] : 0.0f, res.y + 0.5f >= 0.0f ? g[1] : 0.0f, res.z + 0.5f >= 0.0f ? g[2] : 0.0f);
-    float* dsh = dL_dshs + (size_t)i * M * 3;
-    float3 dL_ddir = f3(0, 0, 0);
-    for (int k = 0; k < M; k++) {
-        const float bk = k < nb ? b[k] : 0.0f;
-        dsh[3 * k] = bk * dRGB.x; dsh[3 * k + 1] = bk * dRGB.y; dsh[3 * k + 2] = bk * dRGB.z;
-        if (k < nb) {
-            const float u = sh[3 * k] * dRGB.x + sh[3 * k + 1] * dRGB.y + sh[3 * k + 2] * dRGB.z;
-            dL_ddir += u * sh_basis_grad_k(k, dir);
+__global__ void __launch_bounds__(SHF_THREADS) sh_features_bwd_kernel(int P, int D, int M, int E, const float* __restrict__ means,
+                                                                      const float* __restrict__ shs, const float* __restrict__ campos,
+                                                                      const float* __restrict__ dL_dout, float* __restrict__ dL_dmeans,
+                                                                      float* __restrict__ dL_dshs, float* __restrict__ dL_dextra) {
+    __shared__ float s_tile[(SHF_THREADS / 32) * 32 * (SHF_MAXROW + 1)];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int warp_first = blockIdx.x * SHF_THREADS + warp * 32;
+    if (warp_first >= P) return;
+    const int row = M * 3;
+    float* tile = s_tile + warp * 32 * (SHF_MAXROW + 1);
+    shf_tile_load(shs, P, row, warp_first, lane, tile);
+    __syncwarp();
+    const int i = warp_first + lane;
+    if (i < P) {
+        const float3 dir_orig = ld3(means, i) - f3(campos[0], campos[1], campos[2]);
+        const float len = fmaxf(length3(dir_orig), 1e-12f);
+        const float3 dir = dir_orig / len;
+        float b[16];
+        sh_basis(D, dir, b);
+        const int nb = (D + 1) * (D + 1);
+        float* sh = tile + lane * (row + 1);     // coefficients in, their gradients out (same slot, this thread only)
+        float3 res = f3(0, 0, 0);
+        for (int k = 0; k < nb; k++) res += b[k] * f3(sh[3 * k], sh[3 * k + 1], sh[3 * k + 2]);
+        const float* g = dL_dout + (size_t)i * (3 + E);
+        // clamp_min(x + 0.5, 0): gradient passes where the pre-clamp value is >= 0
+        const float3 dRGB = f3(res.x + 0.5f >= 0.0f ? g[0] : 0.0f, res.y + 0.5f >= 0.0f ? g[1] : 0.0f, res.z + 0.5f >= 0.0f ? g[2] : 0.0f);
+        float3 dL_ddir = f3(0, 0, 0);
+        for (int k = 0; k < M; k++) {
+            const float bk = k < nb ? b[k] : 0.0f;
+            if (k < nb) {
+                const float u = sh[3 * k] * dRGB.x + sh[3 * k + 1] * dRGB.y + sh[3 * k + 2] * dRGB.z;
+                dL_ddir += u * sh_basis_grad_k(k, dir);
+            }
+            sh[3 * k] = bk * dRGB.x; sh[3 * k + 1] = bk * dRGB.y; sh[3 * k + 2] = bk * dRGB.z;
         }
+        const float3 dm = dnormvdv(dir_orig, dL_ddir);
+        dL_dmeans[3 * (size_t)i] = dm.x; dL_dmeans[3 * (size_t)i + 1] = dm.y; dL_dmeans[3 * (size_t)i + 2] = dm.z;
+        for (int e = 0; e < E; e++) dL_dextra[(size_t)i * E + e] = g[3 + e];
     }
-    const float3 dm = dnormvdv(dir_orig, dL_ddir);
-    dL_dmeans[3 * (size_t)i] = dm.x; dL_dmeans[3 * (size_t)i + 1] = dm.y; dL_dmeans[3 * (size_t)i + 2] = dm.z;
-    for (int e = 0; e < E; e++) dL_dextra[(size_t)i * E + e] = g[3 + e];
+    __syncwarp();
+    shf_tile_store(dL_dshs, P, row, warp_first, lane, tile);
 }
 
 int sh_features_forward_impl(int P, int D, int M, int E, const float* means, const float* shs, const float* extra, const float* campos,
                              float* out, cudaStream_t stream) {
     if (P <= 0) return ENVGS_OK;
     ENVGS_TIMED("sh_features_fwd", stream);
-    sh_features_fwd_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, D, M, E, means, shs, extra, campos, out);
+    sh_features_fwd_kernel<<<(P + SHF_THREADS - 1) / SHF_THREADS, SHF_THREADS, 0, stream>>>(P, D, M, E, means, shs, extra, campos, out);
     ENVGS_LAUNCH_CHECK("sh_features_fwd", false, stream);
     return ENVGS_OK;
 }
@@ -96,7 +153,7 @@ int sh_features_backward_impl(int P, int D, int M, int E, const float* means, co
                               float* dL_dmeans, float* dL_dshs, float* dL_dextra, cudaStream_t stream) {
     if (P <= 0) return ENVGS_OK;
     ENVGS_TIMED("sh_features_bwd", stream);
-    sh_features_bwd_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, D, M, E, means, shs, campos, dL_dout, dL_dmeans, dL_dshs, dL_dextra);
+    sh_features_bwd_kernel<<<(P + SHF_THREADS - 1) / SHF_THREADS, SHF_THREADS, 0, stream>>>(P, D, M, E, means, shs, campos, dL_dout, dL_dmeans, dL_dshs, dL_dextra);
     ENVGS_LAUNCH_CHECK("sh_features_bwd", false, stream);
     return ENVGS_OK;
 }

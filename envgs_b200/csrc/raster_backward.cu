@@ -1,8 +1,10 @@
 // raster_backward.cu — backward pass of the surfel rasterizer for sm_100a.
 //
 //   render_bwd_kernel      per tile, back-to-front re-walk of the instance list (RAST5/cuda_rasterizer/backward.cu:143-440).
-//                          Per-(pixel,surfel) partial gradients are reduced warp -> CTA (shared memory) -> one
-//                          global atomic per (tile, surfel, component) instead of the reference's per-pixel atomics.
+//                          Per-(pixel,surfel) partial gradients are reduced across the warp's 32 pixels (split-reduce) and
+//                          each component leaves as ONE fire-and-forget global reduction per (warp, surfel) instead of
+//                          the reference's per-pixel atomics.  (Staging the 8 warps' sums in shared memory first cost
+//                          more than it saved: shared fp32 atomics are CAS loops on sm_100.)
 //   preprocess_bwd_kernel  per surfel chain rule dL/dT, dL/dnormal, dL/dmean2D -> mean/scale/quat (+SH)
 //                          (backward.cu:443-630), including the densification-signal overwrite (:626-629).
 #include "raster_state.cuh"
@@ -28,7 +30,6 @@ __global__ void __launch_bounds__(256, RBWD_MINBLOCKS) render_bwd_kernel(
     __shared__ short4 s_box[BB];
     __shared__ int s_id[BB];
     __shared__ float s_feat[BB * C];
-    __shared__ float s_g[BB * NG];
     __shared__ uint32_t s_max;
 
     const int tile = blockIdx.x;
@@ -54,11 +55,22 @@ __global__ void __launch_bounds__(256, RBWD_MINBLOCKS) render_bwd_kernel(
         uint32_t m = __reduce_max_sync(0xffffffffu, last_contributor);
         if (lane == 0) atomicMax(&s_max, m);
     }
-    for (int k = tid; k < BB * NG; k += 256) s_g[k] = 0.0f;
     __syncthreads();
     const int total = (int)s_max;   // entries beyond the tile-wide last contributor are never visited
     if (total == 0) return;
     const uint32_t warp_last = __reduce_max_sync(0xffffffffu, last_contributor);
+    const int my_comp = warp_split_component<NG>(lane);   // the component whose warp sum this lane ends up with
+    // destination of this lane's component: base pointer + per-surfel stride
+    float* my_dst = nullptr;
+    int my_stride = 0;
+    {
+        const int q = my_comp;
+        if (q >= 0 && q < C) { my_dst = dL_dcolors + q; my_stride = C; }
+        else if (q < C + 3) { my_dst = dL_dnormal3D + (q - C); my_stride = 3; }
+        else if (q == C + 3) { my_dst = dL_dopacity; my_stride = 1; }
+        else if (q < C + 13) { my_dst = dL_dtransMat + (q - C - 4); my_stride = 9; }
+        else { my_dst = dL_dmean2D + (q - C - 13); my_stride = 3; }
+    }
 
     float accum_rec[C], dL_dpixel[C], last_color[C];
 #pragma unroll
@@ -215,28 +227,10 @@ __global__ void __launch_bounds__(256, RBWD_MINBLOCKS) render_bwd_kernel(
                 }
             }
             if (!__any_sync(0xffffffffu, contrib)) continue;
-            // warp -> CTA reduction: transpose-reduce (lane q ends up with the warp sum of component q), one shared atomic per lane
-            const float tot = warp_transpose_reduce<NG>(g, lane);
-            if (lane < NG && tot != 0.0f) atomicAdd(&s_g[j * NG + lane], tot);
+            // split-reduce: each component's warp sum lands in one lane, which adds it to the surfel's gradient row (REDG.ADD.F32)
+            const float tot = warp_split_reduce<NG>(g, lane);
+            if (my_comp >= 0 && tot != 0.0f) atomicAdd(my_dst + (size_t)s_id[j] * my_stride, tot);
         }
-        }
-        __syncthreads();
-        // flush this batch: thread t owns surfel slot t
-        if (tid < nb) {
-            const int id = s_id[tid];
-            float* sg = s_g + tid * NG;
-#pragma unroll
-            for (int q = 0; q < NG; q++) {
-                float v = sg[q];
-                if (v != 0.0f) {
-                    sg[q] = 0.0f;
-                    if (q < C) atomicAdd(&dL_dcolors[(size_t)id * C + q], v);
-                    else if (q < C + 3) atomicAdd(&dL_dnormal3D[(size_t)id * 3 + (q - C)], v);
-                    else if (q == C + 3) atomicAdd(&dL_dopacity[id], v);
-                    else if (q < C + 13) atomicAdd(&dL_dtransMat[(size_t)id * 9 + (q - C - 4)], v);
-                    else atomicAdd(&dL_dmean2D[(size_t)id * 3 + (q - C - 13)], v);
-                }
-            }
         }
         __syncthreads();
     }

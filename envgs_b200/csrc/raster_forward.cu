@@ -277,7 +277,6 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(
     __shared__ short4 s_box[RB];
     __shared__ int s_id[RB];
     __shared__ float s_feat[RB * C];
-    __shared__ float s_wacc[RB];
 
     const int tile = blockIdx.x;
     const int tx = tile % tiles_x, ty = tile / tiles_x;
@@ -302,7 +301,6 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(
     for (int ch = 0; ch < C; ch++) Cacc[ch] = 0.0f;
     float N0 = 0, N1 = 0, N2 = 0, Dacc = 0, M1 = 0, M2 = 0, distortion = 0, median_depth = 0;
 
-    s_wacc[tid] = 0.0f;
     int toDo = total;
     for (int i = 0; i < rounds; i++, toDo -= RB) {
         if (__syncthreads_count(done) == RB) break;
@@ -383,19 +381,15 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(
                     }
                 }
             }
-            // per-surfel accumulated blend weight (forward.cu:420): warp-reduce, then one shared atomic
+            // per-surfel accumulated blend weight (forward.cu:420): warp-reduce, then one global reduction per (warp, surfel)
             if (__any_sync(0xffffffffu, contrib)) {
                 float ws = warp_sum(w);
-                if (lane == 0) atomicAdd(&s_wacc[j], ws);
+                if (lane == 0) atomicAdd(&out_weight[s_id[j]], ws);
             }
             warp_done = __all_sync(0xffffffffu, done);
         }
         }
         __syncthreads();
-        if (tid < nb) {
-            float ws = s_wacc[tid];
-            if (ws != 0.0f) { atomicAdd(&out_weight[s_id[tid]], ws); s_wacc[tid] = 0.0f; }
-        }
     }
 
     if (inside) {

@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(TF_THREADS, T4_MINBLOCKS) traverse_kernel(cons
             const unsigned int hm = (__ballot_sync(0xffffffffu, hit) >> gshift) & 0xFu;
             if (hit) {
                 const int slot = cnt + __popc(hm & lower);
-                if (slot < TF_MAXHITS) p.hits[ray * TF_MAXHITS + slot] = make_float2(t, __int_as_float(sid));
+                if (slot < TF_MAXHITS) __stcs(p.hits + ray * TF_MAXHITS + slot, make_float2(t, __int_as_float(sid)));
             }
             cnt += __popc(hm);
             if (cnt >= TF_MAXHITS && !overflow) { overflow = true; sp = 0; node = STACK_EMPTY; nodeB = STACK_EMPTY; nleaf = 0; }   // full chunk: general kernel
@@ -353,6 +353,13 @@ __device__ __forceinline__ void seg_bitonic_sort(float& t, int& id, int h) {
     }
 }
 
+// 256-bit read-only global load (32-byte aligned address)
+__device__ __forceinline__ void ldg256(const float* p, float* v) {
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
+}
+
 struct HitEval {
     bool contrib;          // passes every test and lies before the termination point
     float alpha, G, w, T_prev, cmd, opac;
@@ -425,17 +432,53 @@ __device__ __forceinline__ float eval_and_scan(const envgs_trace_args& a, bool v
     if (last < 0) T_final = 1.0f;
 
     if (e.contrib) {   // colour and auxiliaries only where they are used
+#ifdef EXP_NO_SH
+        if (false) {
+            const float* sh = a.shs;
+#else
         if (a.colors_precomp == nullptr) {
             const float* sh = a.shs + (size_t)gidx * a.sh_coeffs * 3;
+#endif
             float3 res = f3(0, 0, 0);
             float gr = 0.0f, gg = 0.0f, gb = 0.0f;
-            if (sh_vec4) {
-                const float4* s4 = reinterpret_cast<const float4*>(sh);
-                float tmp[48];
+            const bool sh_vec8 = sh_vec4 && ((a.sh_coeffs * 3) % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.shs) & 31) == 0);
+            if (sh_vec8 && shU == nullptr) {
+                // forward, 256-bit loads (LDG.E.256, new on sm_100): one request per 32-byte sector of the 192-byte row
+                // instead of two 128-bit requests — the rows of a warp's 32 hits are scattered, so the kernel is bound by L1
+                // request slots, not bytes.  Each chunk is consumed as it arrives: flat element f = 8q+i is coefficient f/3
+                // of channel f%3 (same summation order per channel as the scalar path).
+                float acc[3] = {0.0f, 0.0f, 0.0f};
 #pragma unroll
-                for (int q = 0; q < 12; q++) {
-                    if (q * 4 < nbasis * 3) { float4 v = __ldg(&s4[q]); tmp[4 * q] = v.x; tmp[4 * q + 1] = v.y; tmp[4 * q + 2] = v.z; tmp[4 * q + 3] = v.w; }
-                    else { tmp[4 * q] = tmp[4 * q + 1] = tmp[4 * q + 2] = tmp[4 * q + 3] = 0.0f; }
+                for (int q = 0; q < 6; q++) {
+                    if (q * 8 < nbasis * 3) {
+                        float v8[8];
+                        ldg256(sh + 8 * q, v8);
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            const int k = (8 * q + i) / 3;
+                            if (k < nbasis) acc[(8 * q + i) % 3] = fmaf(basis[k], v8[i], acc[(8 * q + i) % 3]);
+                        }
+                    }
+                }
+                res = f3(acc[0] + 0.5f, acc[1] + 0.5f, acc[2] + 0.5f);
+            } else if (sh_vec4) {
+                float tmp[48];
+                if (sh_vec8) {
+#pragma unroll
+                    for (int q = 0; q < 6; q++) {
+                        if (q * 8 < nbasis * 3) ldg256(sh + 8 * q, tmp + 8 * q);
+                        else {
+#pragma unroll
+                            for (int i = 0; i < 8; i++) tmp[8 * q + i] = 0.0f;
+                        }
+                    }
+                } else {
+                    const float4* s4 = reinterpret_cast<const float4*>(sh);
+#pragma unroll
+                    for (int q = 0; q < 12; q++) {
+                        if (q * 4 < nbasis * 3) { float4 v = __ldg(&s4[q]); tmp[4 * q] = v.x; tmp[4 * q + 1] = v.y; tmp[4 * q + 2] = v.z; tmp[4 * q + 3] = v.w; }
+                        else { tmp[4 * q] = tmp[4 * q + 1] = tmp[4 * q + 2] = tmp[4 * q + 3] = 0.0f; }
+                    }
                 }
 #pragma unroll
                 for (int k = 0; k < 16; k++)
@@ -490,8 +533,11 @@ __global__ void __launch_bounds__(256) shade_empty_kernel(const FastParams p) {
     }
 }
 
+#ifndef SFWD_MINBLOCKS
+#define SFWD_MINBLOCKS 5
+#endif
 template <int L>
-__global__ void __launch_bounds__(256) shade_fwd_kernel(const FastParams p, int cls) {
+__global__ void __launch_bounds__(256, SFWD_MINBLOCKS) shade_fwd_kernel(const FastParams p, int cls) {
     constexpr int RPW = 32 / L;              // rays per warp
     constexpr int VPL = 16 / L;              // reduced components per lane
     const envgs_trace_args& a = p.a;
@@ -506,19 +552,44 @@ __global__ void __launch_bounds__(256) shade_fwd_kernel(const FastParams p, int 
     const unsigned int warps_total = (gridDim.x * blockDim.x) >> 5;
     const unsigned int n_items = (n + RPW - 1) / RPW;
 
-    for (unsigned int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < n_items; item += warps_total) {
-        const unsigned int li = item * RPW + (lane / L);
-        const bool live = li < n;
-        const size_t ray = live ? (size_t)list[li] : 0;
-        const int cnt = live ? p.counts[ray] : 0;
-        const float3 ray_o = ld3(a.ray_o, (int)ray), ray_d = ld3(a.ray_d, (int)ray);
+    // Software pipeline over the warp's items: the chain list -> ray -> (count, hit, origin, direction) -> surfel -> SH row is
+    // five dependent memory round trips; the first three are issued one and two items ahead so that only the surfel and SH
+    // fetches are exposed (ncu before: 13.6 long-scoreboard stall cycles per issued instruction at 35 % issue utilisation).
+    struct RayPre { int cnt; float2 hit; float3 o, d; };
+    auto fetch_ray = [&](unsigned int it) -> int {
+        const unsigned int li = it * RPW + (lane / L);
+        return (it < n_items && li < n) ? list[li] : -1;
+    };
+    auto fetch_pre = [&](int r) -> RayPre {
+        RayPre q;
+        const size_t rr = r < 0 ? 0 : (size_t)r;
+        // per-ray data is read once: streaming (evict-first) accesses keep the 60 MB surfel set resident in the 126 MB L2
+        q.cnt = __ldcs(p.counts + rr);
+        q.hit = __ldcs(p.hits + rr * TF_MAXHITS + h);          // slots >= cnt hold stale bytes; masked below
+        q.o = f3(__ldcs(a.ray_o + 3 * rr), __ldcs(a.ray_o + 3 * rr + 1), __ldcs(a.ray_o + 3 * rr + 2));
+        q.d = f3(__ldcs(a.ray_d + 3 * rr), __ldcs(a.ray_d + 3 * rr + 1), __ldcs(a.ray_d + 3 * rr + 2));
+        return q;
+    };
+    unsigned int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int ray_cur = fetch_ray(item), ray_nxt = fetch_ray(item + warps_total);
+    RayPre pre_cur = fetch_pre(ray_cur);
+    for (; item < n_items; item += warps_total) {
+        const int ray_nn = fetch_ray(item + 2 * warps_total);
+        const RayPre pre_nxt = fetch_pre(ray_nxt);
+        const bool live = ray_cur >= 0;
+        const size_t ray = live ? (size_t)ray_cur : 0;
+        const int cnt = live ? pre_cur.cnt : 0;
+        const float3 ray_o = pre_cur.o, ray_d = pre_cur.d;
         float basis[16];
         if (use_sh) sh_basis(a.sh_degree, normalize3(ray_d), basis);
         const bool valid = live && h < cnt;
         float hit_t = TR_DEPTH_INF * 4.0f;
         int hit_id = 0x7fffffff;
-        if (valid) { const float2 hit = p.hits[ray * TF_MAXHITS + h]; hit_t = hit.x; hit_id = __float_as_int(hit.y); }
+        if (valid) { hit_t = pre_cur.hit.x; hit_id = __float_as_int(pre_cur.hit.y); }
+        ray_cur = ray_nxt; ray_nxt = ray_nn; pre_cur = pre_nxt;
+#ifndef EXP_NO_SORT
         seg_bitonic_sort<L>(hit_t, hit_id, h);       // slots [0,cnt) now hold the hits in ascending distance
+#endif
         HitEval e;
         const float T_final = eval_and_scan<L>(a, valid, hit_t, hit_id, ray_o, ray_d, basis, nbasis, sh_vec4, campos, h, e);
 
@@ -535,10 +606,15 @@ __global__ void __launch_bounds__(256) shade_fwd_kernel(const FastParams p, int 
         v[13] = e.w * e.c.x; v[14] = e.w * e.c.y; v[15] = e.w * e.c.z;
         reduce16<L>(v, h);   // v[j], j < VPL: ray-wide sum of component reduce_base(h) + j  (components follow the mid_val layout)
 
+#ifdef EXP_NO_STORE
+        if (live && v[0] == 123.456f) {
+#else
         if (live) {
+#endif
             if (a.training && e.contrib) atomicAdd(&p.o.a_weights[e.gidx], e.w);
             float* mid = p.o.mid_val + ray * 32;
             const int base = reduce_base<L>(h);
+            float mvs[VPL];
 #pragma unroll
             for (int j = 0; j < VPL; j++) {
                 const int c = base + j;    // mid_val slot (config.h:18-26): 0-2 ray_o, 3-5 ray_d, 6 D, 7 A, 8-10 N, 11-12 aux, 13-15 rgb (+T*bg)
@@ -549,14 +625,28 @@ __global__ void __launch_bounds__(256) shade_fwd_kernel(const FastParams p, int 
                 else if (c == 7) mv = 1.0f - T_final;
                 else if (c >= 13) mv = tot + T_final * a.background[c - 13];
                 else mv = tot;
-                mid[c] = mv;
-                mid[16 + c] = 0.0f;
-                if (c < 3) p.o.out_dist[ray * 3 + c] = tot;                 // dist, M1, M2
-                else if (c == 6) p.o.out_dpt[ray] = mv;
-                else if (c == 7) p.o.out_acc[ray] = mv;
-                else if (c >= 8 && c <= 10) p.o.out_norm[ray * 3 + (c - 8)] = mv;
-                else if (c == 11 || c == 12) p.o.out_aux[ray * 2 + (c - 11)] = mv;
-                else if (c >= 13) p.o.out_rgb[ray * 3 + (c - 13)] = mv;     // max_trace_depth == 0: f_this = s_prod = 1
+                mvs[j] = mv;
+#ifdef EXP_NO_OUTS
+                if (mv == 123.456f)
+#endif
+                if (c < 3) __stcs(p.o.out_dist + ray * 3 + c, tot);                 // dist, M1, M2
+                else if (c == 6) __stcs(p.o.out_dpt + ray, mv);
+                else if (c == 7) __stcs(p.o.out_acc + ray, mv);
+                else if (c >= 8 && c <= 10) __stcs(p.o.out_norm + ray * 3 + (c - 8), mv);
+                else if (c == 11 || c == 12) __stcs(p.o.out_aux + ray * 2 + (c - 11), mv);
+                else if (c >= 13) __stcs(p.o.out_rgb + ray * 3 + (c - 13), mv);     // max_trace_depth == 0: f_this = s_prod = 1
+            }
+            // the ray's 128-byte mid_val row (second segment zeroed) leaves as VPL-wide vector stores: the ray's L lanes
+            // cover one contiguous 64-byte half each
+            if (VPL == 4) {
+                __stcs(reinterpret_cast<float4*>(mid + base), make_float4(mvs[0], mvs[1 % VPL], mvs[2 % VPL], mvs[3 % VPL]));
+                __stcs(reinterpret_cast<float4*>(mid + 16 + base), make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+            } else if (VPL == 2) {
+                __stcs(reinterpret_cast<float2*>(mid + base), make_float2(mvs[0], mvs[1 % VPL]));
+                __stcs(reinterpret_cast<float2*>(mid + 16 + base), make_float2(0.0f, 0.0f));
+            } else {
+                __stcs(mid + base, mvs[0]);
+                __stcs(mid + 16 + base, 0.0f);
             }
         }
     }
@@ -588,8 +678,11 @@ __device__ __forceinline__ float3 sh_basis_grad(int k, float3 d) {
 
 constexpr int GR_STRIDE = 20;   // floats per staged hit-gradient record
 
+#ifndef SBWD_MINBLOCKS
+#define SBWD_MINBLOCKS 2
+#endif
 template <int L>
-__global__ void __launch_bounds__(256, 2) shade_bwd_kernel(const FastParams p, int cls) {
+__global__ void __launch_bounds__(256, SBWD_MINBLOCKS) shade_bwd_kernel(const FastParams p, int cls) {
     // per-hit gradient records staged in shared memory so the 61 atomics of a contributing hit are issued by all lanes of
     // the ray instead of one lane after another
     constexpr int RPW = 32 / L;
@@ -620,33 +713,53 @@ __global__ void __launch_bounds__(256, 2) shade_bwd_kernel(const FastParams p, i
         const int cnt = in_list ? p.counts[ray] : 0;
         // saved forward state of the (only) segment
         const float* mid = g.mid_val + ray * 32;
-        const float3 ray_o = f3(mid[MID_RAYO], mid[MID_RAYO + 1], mid[MID_RAYO + 2]);
-        const float3 ray_d = f3(mid[MID_RAYD], mid[MID_RAYD + 1], mid[MID_RAYD + 2]);
+        const float3 ray_o = f3(__ldcs(mid + MID_RAYO), __ldcs(mid + MID_RAYO + 1), __ldcs(mid + MID_RAYO + 2));
+        const float3 ray_d = f3(__ldcs(mid + MID_RAYD), __ldcs(mid + MID_RAYD + 1), __ldcs(mid + MID_RAYD + 2));
         // backward.cu:952-957 with i = 0: s_prev = 1
         const bool live = in_list && !(length3(ray_d) == 0.0f || 1.0f <= a.specular_threshold);
-        const float seg_rgb[3] = {mid[MID_RGB], mid[MID_RGB + 1], mid[MID_RGB + 2]};
-        const float seg_dpt = mid[MID_DPT], seg_acc = mid[MID_ACC];
-        const float3 seg_norm = f3(mid[MID_NORM], mid[MID_NORM + 1], mid[MID_NORM + 2]);
-        const float seg_aux[2] = {mid[MID_AUX], mid[MID_AUX + 1]};
-        const float dL_drgb[3] = {g.dL_drgb[ray * 3], g.dL_drgb[ray * 3 + 1], g.dL_drgb[ray * 3 + 2]};
-        const float dL_ddpt = g.dL_ddpt[ray];
+        const float seg_rgb[3] = {__ldcs(mid + MID_RGB), __ldcs(mid + MID_RGB + 1), __ldcs(mid + MID_RGB + 2)};
+        const float seg_dpt = __ldcs(mid + MID_DPT), seg_acc = __ldcs(mid + MID_ACC);
+        const float3 seg_norm = f3(__ldcs(mid + MID_NORM), __ldcs(mid + MID_NORM + 1), __ldcs(mid + MID_NORM + 2));
+        const float seg_aux[2] = {__ldcs(mid + MID_AUX), __ldcs(mid + MID_AUX + 1)};
+        const float dL_drgb[3] = {__ldcs(g.dL_drgb + ray * 3), __ldcs(g.dL_drgb + ray * 3 + 1), __ldcs(g.dL_drgb + ray * 3 + 2)};
+        const float dL_ddpt = __ldcs(g.dL_ddpt + ray);
         const float3 dL_dnorm = ld3(g.dL_dnorm, (int)ray);
-        const float dL_daux[2] = {g.dL_daux[ray * 2], g.dL_daux[ray * 2 + 1]};
+        const float dL_daux[2] = {__ldcs(g.dL_daux + ray * 2), __ldcs(g.dL_daux + ray * 2 + 1)};
         const float T_final_saved = 1.0f - seg_acc;
 
         float basis[16];
         const float3 dirn = normalize3(ray_d);
         if (use_sh) sh_basis(a.sh_degree, dirn, basis);
+        float* sb = s_basis + ray_slot * 16;          // the scatter phase reads the basis from shared memory: written now so
+        if (use_sh && h == 0) {                        // the 16 registers die after the colour evaluation
+#pragma unroll
+            for (int k = 0; k < 16; k++) sb[k] = k < nbasis ? basis[k] : 0.0f;
+        }
         const bool valid = live && h < cnt;
         float hit_t = TR_DEPTH_INF * 4.0f;
         int hit_id = 0x7fffffff;
-        if (valid) { const float2 hit = p.hits[ray * TF_MAXHITS + h]; hit_t = hit.x; hit_id = __float_as_int(hit.y); }
+        if (valid) { const float2 hit = __ldcs(p.hits + ray * TF_MAXHITS + h); hit_t = hit.x; hit_id = __float_as_int(hit.y); }
         seg_bitonic_sort<L>(hit_t, hit_id, h);
         HitEval e;
         float shU[16];
 #pragma unroll
         for (int k = 0; k < 16; k++) shU[k] = 0.0f;
         eval_and_scan<L>(a, valid, hit_t, hit_id, ray_o, ray_d, basis, nbasis, sh_vec4, campos, h, e, dL_drgb, use_sh ? shU : nullptr);
+        // SH direction gradient (done first: it retires the 16 shU registers before the long gradient chain): dL/ddir = sum_k U_k * grad basis_k(dir), U_k = sum over hits of shU[k]
+        float3 extra = f3(0, 0, 0);
+        if (use_sh) {
+            reduce16<L>(shU, h);
+            const int base = reduce_base<L>(h);
+            float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+#pragma unroll
+            for (int j = 0; j < VPL; j++) {
+                const int k = base + j;
+                const float3 gb = sh_basis_grad(k < nbasis ? k : 0, dirn);
+                sx += shU[j] * gb.x; sy += shU[j] * gb.y; sz += shU[j] * gb.z;
+            }
+            sx = seg_sum<L>(sx); sy = seg_sum<L>(sy); sz = seg_sum<L>(sz);
+            if (live) extra = dnormvdv(ray_d, f3(sx, sy, sz));   // backward.cu:182-184
+        }
 
         // inclusive prefix sums the reference keeps in C, O, D, N while walking front to back
         const float Cx = seg_scan_add<L>(e.w * e.c.x, h), Cy = seg_scan_add<L>(e.w * e.c.y, h), Cz = seg_scan_add<L>(e.w * e.c.z, h);
@@ -720,13 +833,11 @@ __global__ void __launch_bounds__(256, 2) shade_bwd_kernel(const FastParams p, i
         }
         // ---- cooperative scatter: the ray's lanes walk its contributing hits; lane q takes components q, q+L, ... ----
         {
-            float* sb = s_basis + ray_slot * 16;
-            if (use_sh && h == 0) {
-#pragma unroll
-                for (int k = 0; k < 16; k++) sb[k] = k < nbasis ? basis[k] : 0.0f;
-            }
             __syncwarp();
             unsigned int cm = (__ballot_sync(0xffffffffu, e.contrib) >> seg_shift) & seg_mask;
+#ifdef EXP_BWD_NO_SCATTER
+            if (ray == 0x7fffffffu)
+#endif
             while (__any_sync(0xffffffffu, cm != 0u)) {
                 if (cm != 0u) {
                     const int hit = __ffs(cm) - 1;
@@ -770,22 +881,11 @@ __global__ void __launch_bounds__(256, 2) shade_bwd_kernel(const FastParams p, i
 #pragma unroll
         for (int i = 6; i < 16; i++) v[i] = 0.0f;
         reduce16<L>(v, h);
-        // SH direction gradient: dL/ddir = sum_k U_k * grad basis_k(dir), U_k = sum over hits of shU[k]
-        float3 extra = f3(0, 0, 0);
-        if (use_sh) {
-            reduce16<L>(shU, h);
-            const int base = reduce_base<L>(h);
-            float sx = 0.0f, sy = 0.0f, sz = 0.0f;
-#pragma unroll
-            for (int j = 0; j < VPL; j++) {
-                const int k = base + j;
-                const float3 gb = sh_basis_grad(k < nbasis ? k : 0, dirn);
-                sx += shU[j] * gb.x; sy += shU[j] * gb.y; sz += shU[j] * gb.z;
-            }
-            sx = seg_sum<L>(sx); sy = seg_sum<L>(sy); sz = seg_sum<L>(sz);
-            if (live) extra = dnormvdv(ray_d, f3(sx, sy, sz));   // backward.cu:182-184
-        }
+#ifdef EXP_BWD_NO_RAYGRAD
+        if (in_list && ray == 0x7fffffffu) {
+#else
         if (in_list) {
+#endif
             const int base = reduce_base<L>(h);
 #pragma unroll
             for (int j = 0; j < VPL; j++) {

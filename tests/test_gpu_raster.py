@@ -156,7 +156,7 @@ def test_fused_sh_features_match_pytorch(built_lib):
     """envgs_sh_features_* (caller-side glue) vs the PyTorch expressions EasyVolcap uses."""
     from envgs_b200.features import sh_features
     from envgs_b200.pipeline import eval_sh_deg3
-    base = scene.make_base_set(20000, seed=3).to("cuda")
+    base = scene.make_base_set(20011, seed=3).to("cuda")   # not a multiple of the 32-surfel warp tile
     cam = scene.ring_cameras(1, 64, 64)[0].to("cuda")
     leaf = lambda t: t.clone().requires_grad_(True)
     m1, s1, e1 = leaf(base.means), leaf(base.shs * 3.0), leaf(torch.cat([base.specular, base.roughness], -1))   # x3: exercise the clamp
