@@ -336,8 +336,17 @@ def main():
         t_ms = kernels.get("render_fwd")
         if t_ms:
             ach = alg_bytes / (t_ms * 1e-3) / 1e9
+            traffic, traffic_src = None, None
+            try:                                    # DRAM bytes of this kernel from the committed ncu --set full capture
+                with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+                    tj = json.load(f).get(args.workload)
+                if tj and tj.get("kernel") == "render_fwd_kernel<5>":
+                    traffic, traffic_src = int(tj["traffic"]), tj.get("source")
+            except Exception:
+                pass
             roofline = {"kernel": "render_fwd_kernel<5>", "bound": "hbm", "achieved": round(ach, 2), "peak": peak, "unit": "GB/s",
-                        "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src, "algorithmic_bytes": alg_bytes,
+                        "frac": round(ach / peak, 4), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                        "algorithmic_bytes": alg_bytes,
                         "launch_ms": t_ms, "num_rendered": N, "visible_surfels": P_v,
                         "note": "render_fwd is fp32-issue bound, not HBM bound (SURVEY.md §8d); see DESIGN.md"}
 

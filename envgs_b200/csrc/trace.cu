@@ -192,10 +192,14 @@ __global__ void __launch_bounds__(TR_THREADS) trace_kernel(const TraceParams p) 
         int row, col;
         bool listed = true;
         if (p.ray_list != nullptr) {
+            // Listed rays are the long ones (>= 16 hits) and few: they are spread over as many warps as the grid has —
+            // 32 of them in one warp would serialise 32 divergent traversals (measured: 107 rays took 1.1 ms that way).
             const unsigned int n = *p.ray_count;
-            if (item >= (n + 31u) / 32u) break;
-            const unsigned int k = item * 32u + lane;
-            listed = k < n;
+            const unsigned int warps = gridDim.x * (TR_THREADS / 32);
+            const unsigned int rpw = min(32u, (n + warps - 1u) / warps);   // rays per warp (>= 1 when n > 0)
+            if (n == 0u || item >= (n + rpw - 1u) / rpw) break;
+            const unsigned int k = item * rpw + lane;
+            listed = lane < rpw && k < n;
             const int r = listed ? p.ray_list[k] : 0;
             row = r / W; col = r % W;
         } else if (p.tiles_x > 0) {

@@ -62,7 +62,10 @@ def main(P=1_000_000, H=1080, W=1920, C=5):
         "speedup_fwd": t_rf / t_of, "speedup_bwd": t_rb / t_ob, "speedup_total": (t_rf + t_rb) / (t_of + t_ob),
         "ref_num_rendered": int(rn), "ours_kernels_ms": {k: v[1] / v[0] for k, v in prof.items()},
         "color": Hh.image_report("color", color.cpu(), rcolor.cpu()), "allmap": Hh.image_report("allmap", allmap.detach().cpu(), rallmap.cpu()),
-        "radii_mismatch": int((radii != rradii).sum()), "weight_relL2": Hh.rel_l2(weight.cpu(), rweight.cpu()),
+        "radii_mismatch": int((radii != rradii).sum()), "radii_max_abs_diff": int((radii.long() - rradii.long()).abs().max()),
+        "g_means_trimmed": Hh.trimmed_rel_l2(leafs[0].grad.cpu(), gm3.cpu()), "g_rots_trimmed": Hh.trimmed_rel_l2(leafs[3].grad.cpu(), grot.cpu()),
+        "g_scales_trimmed": Hh.trimmed_rel_l2(leafs[2].grad.cpu(), gsc.cpu()), "g_means2D_trimmed": Hh.trimmed_rel_l2(m2.grad.cpu(), gm2.cpu()),
+        "weight_relL2": Hh.rel_l2(weight.cpu(), rweight.cpu()),
         "g_means": Hh.rel_l2(leafs[0].grad.cpu(), gm3.cpu()), "g_opac": Hh.rel_l2(leafs[1].grad.cpu(), gop.cpu()),
         "g_scales": Hh.rel_l2(leafs[2].grad.cpu(), gsc.cpu()), "g_rots": Hh.rel_l2(leafs[3].grad.cpu(), grot.cpu()),
         "g_colors": Hh.rel_l2(leafs[4].grad.cpu(), gcol.cpu()), "g_means2D": Hh.rel_l2(m2.grad.cpu(), gm2.cpu()),
