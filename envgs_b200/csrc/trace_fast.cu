@@ -38,6 +38,7 @@ struct FastParams {
     unsigned int* overflow_count; // [1]
     int* overflow_list;           // [R]
     unsigned int* class_count;    // [4] rays with 0 / 1-4 / 5-8 / 9-15 hits
+    unsigned int* block_counts;   // scratch of the class-list kernels
     int* class_list;              // [4][R]
     int R;
     unsigned int* work_counter;
@@ -46,9 +47,12 @@ struct FastParams {
     int refill_threshold;         // leave an inner traversal loop when fewer lanes than this are still in it
 };
 
+constexpr int CL_THREADS = 512;               // rays per block of the class-list kernels
+static inline size_t cl_blocks(size_t R) { return (R + CL_THREADS - 1) / CL_THREADS; }
+
 size_t trace_cache_bytes(int H, int W) {
     size_t R = (size_t)H * W;
-    return R * (TF_MAXHITS * sizeof(float2) + 4 + 4 + 16) + 1024;
+    return R * (TF_MAXHITS * sizeof(float2) + 4 + 4 + 16) + 1024 + 4 * cl_blocks(R) * sizeof(unsigned int);
 }
 static void carve_cache(char* base, int H, int W, FastParams& p) {
     size_t R = (size_t)H * W;
@@ -59,6 +63,7 @@ static void carve_cache(char* base, int H, int W, FastParams& p) {
     p.class_list = p.overflow_list + R;
     p.overflow_count = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(p.class_list + 4 * R) + 256);
     p.class_count = p.overflow_count + 4;
+    p.block_counts = p.overflow_count + 64;     // [4][cl_blocks(R)] per-block class counts -> offsets
 }
 
 __device__ __forceinline__ float safe_inv_f(float d) { return 1.0f / (fabsf(d) > 1e-30f ? d : copysignf(1e-30f, d)); }
@@ -102,6 +107,13 @@ __device__ __forceinline__ int lds32(unsigned int addr) {
 #ifndef T4_MINBLOCKS
 #define T4_MINBLOCKS 9
 #endif
+__device__ __forceinline__ const Bvh4Slot* node_slot(const char* slot0, int node, bool active) {
+    unsigned long long addr;
+    asm("{\n\t.reg .pred p;\n\t.reg .u32 n;\n\tsetp.ne.u32 p, %2, 0;\n\tselp.u32 n, %1, 0, p;\n\tmad.wide.u32 %0, n, 128, %3;\n\t}"
+        : "=l"(addr) : "r"(node), "r"((unsigned int)active), "l"(reinterpret_cast<unsigned long long>(slot0)));
+    return reinterpret_cast<const Bvh4Slot*>(addr);
+}
+
 template <bool STATS>
 __global__ void __launch_bounds__(TF_THREADS, T4_MINBLOCKS) traverse_kernel(const FastParams p) {
     __shared__ int s_buf[(TF_THREADS / 4) * T4_GROUP];
@@ -129,7 +141,6 @@ __global__ void __launch_bounds__(TF_THREADS, T4_MINBLOCKS) traverse_kernel(cons
         const bool idle = (node == STACK_EMPTY) && nleaf == 0;
         {
             const bool retire = idle && have_ray;
-            int cls = -1;   // 0: no hit, 1: 1-4 hits, 2: 5-8, 3: 9-15 (lanes per ray 4 / 8 / 16 in the shading kernels)
             if (retire && sub == 0) {
                 if (overflow) {
                     p.counts[ray] = -1;
@@ -137,25 +148,11 @@ __global__ void __launch_bounds__(TF_THREADS, T4_MINBLOCKS) traverse_kernel(cons
                     p.overflow_list[k] = (int)ray;
                 } else {
                     p.counts[ray] = cnt;
-                    cls = cnt == 0 ? 0 : (cnt <= 4 ? 1 : (cnt <= 8 ? 2 : 3));
                 }
                 if (STATS) {
                     atomicAdd(&p.stats[0], 1ull); atomicAdd(&p.stats[1], (unsigned long long)st_nodes);
                     atomicAdd(&p.stats[2], (unsigned long long)st_prims); atomicAdd(&p.stats[3], (unsigned long long)cnt);
                     atomicAdd(&p.stats[4], 1ull);
-                }
-            }
-            if (__any_sync(0xffffffffu, cls >= 0)) {   // warp-aggregated append to the per-class ray lists
-#pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    const unsigned int m = __ballot_sync(0xffffffffu, cls == c);
-                    if (m) {
-                        const int leader = __ffs(m) - 1;
-                        unsigned int base = 0;
-                        if (lane == leader) base = atomicAdd(&p.class_count[c], (unsigned int)__popc(m));
-                        base = __shfl_sync(0xffffffffu, base, leader);
-                        if (cls == c) p.class_list[(size_t)c * p.R + base + __popc(m & ((1u << lane) - 1u))] = (int)ray;
-                    }
                 }
             }
             if (retire) have_ray = false;
@@ -199,9 +196,9 @@ __global__ void __launch_bounds__(TF_THREADS, T4_MINBLOCKS) traverse_kernel(cons
             if (am == 0u) break;
             if (can_refill && __popc(am) < p.refill_threshold) break;   // let idle groups fetch new rays (Aila & Laine 2009)
             const bool actB = act && nodeB != STACK_EMPTY;
-            const unsigned int ndA = act ? (unsigned int)node : 0u, ndB = actB ? (unsigned int)nodeB : 0u;
-            const Bvh4Slot* __restrict__ slA = reinterpret_cast<const Bvh4Slot*>(slot0 + ((size_t)ndA << 7));
-            const Bvh4Slot* __restrict__ slB = reinterpret_cast<const Bvh4Slot*>(slot0 + ((size_t)ndB << 7));
+            // idle groups re-test node 0; select-then-widen (selp + mad.wide) instead of the 64-bit selects ptxas derives itself
+            const Bvh4Slot* __restrict__ slA = node_slot(slot0, node, act);
+            const Bvh4Slot* __restrict__ slB = node_slot(slot0, nodeB, actB);
             const float4 A0 = __ldg(&slA->a), A1 = __ldg(&slA->b), B0 = __ldg(&slB->a), B1 = __ldg(&slB->b);
             if (STATS) st_nodes += (act ? 1u : 0u) + (actB ? 1u : 0u);
             bool hitA, hitB;
@@ -277,6 +274,96 @@ __global__ void __launch_bounds__(TF_THREADS, T4_MINBLOCKS) traverse_kernel(cons
         nleaf = 0;
         __syncwarp();
     }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// class lists in pixel order
+// ------------------------------------------------------------------------------------------------------
+// The shading kernels take their rays from four lists (0 / 1-4 / 5-8 / 9-15 hits).  The lists are built AFTER the traversal
+// by a stable three-kernel compaction over counts[] in ray-index order (count -> scan -> scatter, 16 MB of traffic), not
+// appended in retirement order: consecutive list entries are then neighbouring pixels, so a warp's per-ray loads and stores
+// (hit lines, mid_val rows, the AoS outputs, upstream gradients) share sectors, and neighbouring reflection rays fetch
+// overlapping sets of surfels.
+__device__ __forceinline__ int hit_class(int cnt) { return cnt < 0 ? -1 : (cnt == 0 ? 0 : (cnt <= 4 ? 1 : (cnt <= 8 ? 2 : 3))); }
+
+__global__ void __launch_bounds__(CL_THREADS) class_count_kernel(const FastParams p, int nblocks) {
+    __shared__ unsigned int s_cnt[4];
+    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int r = blockIdx.x * CL_THREADS + threadIdx.x;
+    const int cls = r < p.R ? hit_class(p.counts[r]) : -1;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const unsigned int m = __ballot_sync(0xffffffffu, cls == c);
+        if ((threadIdx.x & 31) == 0 && m) atomicAdd(&s_cnt[c], (unsigned int)__popc(m));
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) p.block_counts[(size_t)threadIdx.x * nblocks + blockIdx.x] = s_cnt[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(1024) class_scan_kernel(const FastParams p, int nblocks) {   // one block; counts -> exclusive offsets
+    __shared__ unsigned int s_warp[32];
+    __shared__ unsigned int s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int c = 0; c < 4; c++) {
+        unsigned int* row = p.block_counts + (size_t)c * nblocks;
+        if (threadIdx.x == 0) s_carry = 0;
+        __syncthreads();
+        for (int base = 0; base < nblocks; base += 1024) {
+            const int i = base + threadIdx.x;
+            const unsigned int v = i < nblocks ? row[i] : 0u;
+            unsigned int x = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+            if (lane == 31) s_warp[warp] = x;
+            __syncthreads();
+            if (warp == 0) {
+                unsigned int w = s_warp[lane];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const unsigned int y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+                s_warp[lane] = w;
+            }
+            __syncthreads();
+            const unsigned int incl = x + (warp > 0 ? s_warp[warp - 1] : 0u) + s_carry;
+            if (i < nblocks) row[i] = incl - v;
+            __syncthreads();
+            if (threadIdx.x == 1023) s_carry = incl;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) p.class_count[c] = s_carry;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(CL_THREADS) class_scatter_kernel(const FastParams p, int nblocks) {
+    __shared__ unsigned int s_warp[4][CL_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r = blockIdx.x * CL_THREADS + threadIdx.x;
+    const int cls = r < p.R ? hit_class(p.counts[r]) : -1;
+    unsigned int rank = 0;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const unsigned int m = __ballot_sync(0xffffffffu, cls == c);
+        if (cls == c) rank = __popc(m & ((1u << lane) - 1u));
+        if (lane == 0) s_warp[c][warp] = __popc(m);
+    }
+    __syncthreads();
+    if (cls >= 0) {
+        unsigned int off = p.block_counts[(size_t)cls * nblocks + blockIdx.x];
+        for (int w = 0; w < warp; w++) off += s_warp[cls][w];
+        p.class_list[(size_t)cls * p.R + off + rank] = r;
+    }
+}
+
+static int build_class_lists(const FastParams& p, cudaStream_t stream) {
+    const int nblocks = (int)cl_blocks((size_t)p.R);
+    class_count_kernel<<<nblocks, CL_THREADS, 0, stream>>>(p, nblocks);
+    ENVGS_LAUNCH_CHECK("trace_class_count", false, stream);
+    class_scan_kernel<<<1, 1024, 0, stream>>>(p, nblocks);
+    ENVGS_LAUNCH_CHECK("trace_class_scan", false, stream);
+    class_scatter_kernel<<<nblocks, CL_THREADS, 0, stream>>>(p, nblocks);
+    ENVGS_LAUNCH_CHECK("trace_class_scatter", false, stream);
+    return ENVGS_OK;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -946,6 +1033,11 @@ int trace_forward_fast(Lbvh& bvh, unsigned int* counter, unsigned long long* sta
         if (stats) traverse_kernel<true><<<blocks, TF_THREADS, 0, stream>>>(p);
         else traverse_kernel<false><<<blocks, TF_THREADS, 0, stream>>>(p);
         ENVGS_LAUNCH_CHECK("trace_traverse", false, stream);
+    }
+    {
+        ENVGS_TIMED("trace_class_lists", stream);
+        int rcl = build_class_lists(p, stream);
+        if (rcl != ENVGS_OK) return rcl;
     }
     // rays whose first chunk was full: the reference's multi-chunk loop, run by the general kernel on the device-side list
     ENVGS_CUDA_TRY(cudaEventRecord(side.fork, stream));
