@@ -226,7 +226,8 @@ __global__ void __launch_bounds__(256, RBWD_MINBLOCKS) render_bwd_kernel(
                     }
                 }
             }
-            if (!__any_sync(0xffffffffu, contrib)) continue;
+            const unsigned int cb = __ballot_sync(0xffffffffu, contrib);
+            if (cb == 0u) continue;
             // split-reduce: each component's warp sum lands in one lane, which adds it to the surfel's gradient row (REDG.ADD.F32)
             const float tot = warp_split_reduce<NG>(g, lane);
             if (my_comp >= 0 && tot != 0.0f) atomicAdd(my_dst + (size_t)s_id[j] * my_stride, tot);

@@ -765,17 +765,20 @@ __device__ __forceinline__ float3 sh_basis_grad(int k, float3 d) {
 
 constexpr int GR_STRIDE = 20;   // floats per staged hit-gradient record
 
+#ifndef SBWD_THREADS
+#define SBWD_THREADS 256
+#endif
 #ifndef SBWD_MINBLOCKS
 #define SBWD_MINBLOCKS 2
 #endif
 template <int L>
-__global__ void __launch_bounds__(256, SBWD_MINBLOCKS) shade_bwd_kernel(const FastParams p, int cls) {
+__global__ void __launch_bounds__(SBWD_THREADS, SBWD_MINBLOCKS) shade_bwd_kernel(const FastParams p, int cls) {
     // per-hit gradient records staged in shared memory so the 61 atomics of a contributing hit are issued by all lanes of
     // the ray instead of one lane after another
     constexpr int RPW = 32 / L;
     constexpr int VPL = 16 / L;
-    __shared__ float s_rec[256 * GR_STRIDE];             // one record per thread (= per hit slot)
-    __shared__ float s_basis[(256 / L) * 16];
+    __shared__ float s_rec[SBWD_THREADS * GR_STRIDE];    // one record per thread (= per hit slot)
+    __shared__ float s_basis[(SBWD_THREADS / L) * 16];
     const envgs_trace_args& a = p.a;
     const envgs_trace_grads& g = p.g;
     const int lane = threadIdx.x & 31;
@@ -1080,12 +1083,12 @@ int trace_backward_fast(Lbvh& bvh, unsigned int* counter, unsigned long long* st
     ENVGS_CUDA_TRY(cudaEventRecord(side.join, side.stream));
     {
         ENVGS_TIMED("trace_shade_bwd", stream);
-        const int sblocks = sm_count * 2;
-        shade_bwd_kernel<4><<<sblocks, 256, 0, stream>>>(p, 1);
+        const int sblocks = sm_count * SBWD_MINBLOCKS;   // persistent grid-stride kernels: exactly the resident CTAs
+        shade_bwd_kernel<4><<<sblocks, SBWD_THREADS, 0, stream>>>(p, 1);
         ENVGS_LAUNCH_CHECK("trace_shade_bwd4", false, stream);
-        shade_bwd_kernel<8><<<sblocks, 256, 0, stream>>>(p, 2);
+        shade_bwd_kernel<8><<<sblocks, SBWD_THREADS, 0, stream>>>(p, 2);
         ENVGS_LAUNCH_CHECK("trace_shade_bwd8", false, stream);
-        shade_bwd_kernel<16><<<sblocks, 256, 0, stream>>>(p, 3);
+        shade_bwd_kernel<16><<<sblocks, SBWD_THREADS, 0, stream>>>(p, 3);
         ENVGS_LAUNCH_CHECK("trace_shade_bwd16", false, stream);
     }
     ENVGS_CUDA_TRY(cudaStreamWaitEvent(stream, side.join, 0));
