@@ -55,6 +55,8 @@ int glue_reflect_forward(const envgs_glue_camera& cam, const float* allmap, floa
 int glue_reflect_backward(const envgs_glue_camera& cam, const float* allmap, const float* g_ro, const float* g_rd, float* dL_dallmap, cudaStream_t stream);
 int glue_blend_loss_forward(const envgs_glue_camera& cam, const float* image, const float* allmap, const float* env_rgb, const float* target, float lambda_n, float* rgb_out, float* loss2, cudaStream_t stream);
 int glue_blend_loss_backward(const envgs_glue_camera& cam, const float* image, const float* allmap, const float* env_rgb, const float* target, const float* rgb, float lambda_n, const float* g_loss, const float* g_rgb, float* dL_dimage, float* dL_dallmap, float* dL_denv, cudaStream_t stream);
+int adam_step_impl(size_t n, float* p, float* g, float* m, float* v, int step, float lr, float b1, float b2, float eps, float grad_scale,
+                   int zero_grad, cudaStream_t stream);
 int sh_features_forward_impl(int P, int D, int M, int E, const float* means, const float* shs, const float* extra, const float* campos, float* out, cudaStream_t stream);
 int sh_features_backward_impl(int P, int D, int M, int E, const float* means, const float* shs, const float* campos, const float* dL_dout, float* dL_dmeans, float* dL_dshs, float* dL_dextra, cudaStream_t stream);
 bool trace_fast_eligible(const envgs_trace_args& a, const void* cache);
@@ -342,6 +344,17 @@ int envgs_trace_backward(envgs_tracer* h, const envgs_trace_args* args, const en
     if (trace_fast_eligible(*args, g->hit_cache))
         return trace_backward_fast(h->bvh, h->counter, h->stats(), *args, *g, g->hit_cache, (cudaStream_t)stream, h->side);
     return trace_backward_impl(h->bvh, h->counter, h->stats(), *args, *g, (cudaStream_t)stream);
+}
+
+int envgs_adam_step(uint64_t n, float* params, float* grads, float* exp_avg, float* exp_avg_sq, int32_t step, float lr, float beta1,
+                    float beta2, float eps, float grad_scale, int32_t zero_grad, void* stream) {
+    if (n > 0 && (!params || !grads || !exp_avg || !exp_avg_sq)) { set_error("adam_step pointer is NULL"); return ENVGS_ERR_INVALID; }
+    if (step < 1 || !(beta1 >= 0.0f && beta1 < 1.0f) || !(beta2 >= 0.0f && beta2 < 1.0f)) { set_error("bad adam_step arguments step=%d beta1=%g beta2=%g", step, beta1, beta2); return ENVGS_ERR_INVALID; }
+    if ((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) | reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15) {
+        set_error("adam_step buffers must be 16-byte aligned");
+        return ENVGS_ERR_INVALID;
+    }
+    return adam_step_impl((size_t)n, params, grads, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps, grad_scale, zero_grad, (cudaStream_t)stream);
 }
 
 }  // extern "C"

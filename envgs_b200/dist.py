@@ -68,8 +68,29 @@ def shard_views(n_views: int, rank: int, world: int) -> list[int]:
     return list(range(rank, n_views, world))
 
 
+class FlatAdam:
+    """Adam over the flat buffers in ONE kernel (`envgs_adam_step`): gradient scaling (the 1/world average), moment and
+    parameter update and the zero-fill of the gradient buffer for the next step.  CUDA only; arithmetic of
+    torch.optim.Adam(fused=True) without weight decay (the reference: EVC/runners/optimizers.py:163-201)."""
+
+    def __init__(self, flat: torch.Tensor, flat_grad: torch.Tensor, lr: float, betas=(0.9, 0.999), eps: float = 1e-15):
+        assert flat.is_cuda and flat.dtype == torch.float32 and flat.is_contiguous() and flat_grad.is_contiguous()
+        self.flat, self.flat_grad, self.lr, self.betas, self.eps = flat, flat_grad, lr, betas, eps
+        self.exp_avg, self.exp_avg_sq = torch.zeros_like(flat), torch.zeros_like(flat)
+        self.t = 0
+
+    def step(self, grad_scale: float = 1.0, zero_grad: bool = True) -> None:
+        from . import _lib
+        self.t += 1
+        with torch.cuda.device(self.flat.device):
+            _lib.check(_lib.lib().envgs_adam_step(self.flat.numel(), _lib.ptr(self.flat), _lib.ptr(self.flat_grad), _lib.ptr(self.exp_avg),
+                                                  _lib.ptr(self.exp_avg_sq), self.t, self.lr, self.betas[0], self.betas[1], self.eps,
+                                                  grad_scale, int(zero_grad), torch.cuda.current_stream(self.flat.device).cuda_stream),
+                       "envgs_adam_step")
+
+
 class ViewParallelTrainer:
-    """One optimisation step = every rank renders + differentiates its view, one all-reduce, (optional) fused Adam."""
+    """One optimisation step = every rank renders + differentiates its view, one all-reduce, one fused Adam/scale/zero pass."""
 
     def __init__(self, renderer: nn.Module, lr: float = 1e-4, average: bool = True, optimizer: bool = True):
         self.renderer = renderer
@@ -77,24 +98,33 @@ class ViewParallelTrainer:
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.average = average
         self.opt = None
-        if optimizer:
+        self.fused = None
+        self._grad_is_zero = False
+        if optimizer and self.flat.flat.is_cuda:
+            self.fused = FlatAdam(self.flat.flat, self.flat.flat_grad, lr=lr)
+        elif optimizer:                                  # CPU (gloo tests): torch's Adam over the same flat buffers
             flat_param = nn.Parameter(self.flat.flat, requires_grad=True)
             flat_param.grad = self.flat.flat_grad
-            kw = dict(fused=True) if self.flat.flat.is_cuda else {}
-            self.opt = torch.optim.Adam([flat_param], lr=lr, eps=1e-15, **kw)
+            self.opt = torch.optim.Adam([flat_param], lr=lr, eps=1e-15)
             self._flat_param = flat_param
 
     def step(self, cam, target) -> torch.Tensor:
-        self.flat.zero_grad()
+        if not self._grad_is_zero:                       # the fused update leaves the gradient buffer zeroed for the next step
+            self.flat.zero_grad()
         out = self.renderer(cam, target)
         loss = self.renderer.loss(out, target)
         loss.backward()
         self.flat.collect_stray_grads()
         if self.world > 1:
             dist.all_reduce(self.flat.flat_grad, op=dist.ReduceOp.SUM)   # the single collective of the step
-            if self.average:
-                self.flat.flat_grad.mul_(1.0 / self.world)
-        if self.opt is not None:
-            self._flat_param.grad = self.flat.flat_grad
-            self.opt.step()
+        scale = 1.0 / self.world if (self.world > 1 and self.average) else 1.0
+        if self.fused is not None:
+            self.fused.step(grad_scale=scale, zero_grad=True)
+            self._grad_is_zero = True
+        else:
+            if scale != 1.0:
+                self.flat.flat_grad.mul_(scale)
+            if self.opt is not None:
+                self._flat_param.grad = self.flat.flat_grad
+                self.opt.step()
         return loss.detach()

@@ -239,6 +239,14 @@ int envgs_glue_blend_loss_backward(const envgs_glue_camera* cam, const float* im
                                    const float* target, const float* rgb, float lambda_n, const float* g_loss, const float* g_rgb,
                                    float* dL_dimage, float* dL_dallmap, float* dL_denv, void* stream);
 
+/* Parameter update of the view-parallel step over FLAT fp32 buffers (n elements each, 16-byte aligned): Adam with bias
+ * correction at step `step` (1-based), the gradient pre-multiplied by `grad_scale` (1/world_size after the sum all-reduce) and,
+ * if zero_grad != 0, the gradient buffer cleared for the next step — one pass instead of torch's scale + multi-tensor Adam +
+ * memset.  Same arithmetic as torch.optim.Adam(fused=True) without weight decay / amsgrad.  Replaces: the optimizer step the
+ * reference runs through torch (EVC/runners/optimizers.py:163-201, volumetric_video_runner.py:443). */
+int envgs_adam_step(uint64_t n, float* params, float* grads, float* exp_avg, float* exp_avg_sq, int32_t step, float lr, float beta1,
+                    float beta2, float eps, float grad_scale, int32_t zero_grad, void* stream);
+
 /* Kernel-launch counter (every kernel this library launches increments it); bench.py reports it. */
 uint64_t envgs_launch_count(void);
 

@@ -85,3 +85,29 @@ def test_bench_contract_on_tiny_workload(built_lib):
     assert d["n_gpus"] == 1 and d["steps"] == 4 and d["value"] > 0 and d["gpu_launches"] > 0
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["value"] > 0
     assert "workload" in d["config"] and d["roofline"]["bound"] == "hbm" and 0 < d["roofline"]["frac"] < 1
+
+
+def test_flat_adam_matches_torch_adam(built_lib):
+    """envgs_adam_step (scale + Adam + zero-grad in one pass over the flat buffers) vs torch.optim.Adam on the same numbers."""
+    from envgs_b200.dist import FlatAdam
+    g = torch.Generator(device="cpu").manual_seed(0)
+    n = 4 * 25_000 + 3                                   # exercises the scalar tail
+    store = torch.empty(n + 4, device="cuda")            # 16-byte aligned views of odd length
+    p0 = torch.randn(n, generator=g).cuda()
+    flat, grad = store[:n].copy_(p0), torch.zeros(n + 4, device="cuda")[:n]
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=3e-3, eps=1e-15)
+    mine = FlatAdam(flat, grad, lr=3e-3)
+    for it in range(6):
+        gr = torch.randn(n, generator=g).cuda() * (10.0 ** (it - 3))
+        grad.copy_(gr * 4.0)                             # "sum over 4 ranks"
+        mine.step(grad_scale=0.25, zero_grad=True)
+        assert float(grad.abs().max()) == 0.0
+        ref.grad = gr.clone()
+        opt.step()
+        err = float((flat - ref.detach()).abs().max())
+        assert err <= 2e-6 * max(1.0, float(ref.detach().abs().max())), (it, err)
+    with pytest.raises(RuntimeError):
+        from envgs_b200 import _lib
+        _lib.check(_lib.lib().envgs_adam_step(8, _lib.ptr(flat) + 4, _lib.ptr(grad), _lib.ptr(mine.exp_avg), _lib.ptr(mine.exp_avg_sq), 1,
+                                              1e-3, 0.9, 0.999, 1e-15, 1.0, 0, None), "misaligned")
