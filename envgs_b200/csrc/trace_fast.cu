@@ -4,11 +4,11 @@
 //                     refill, two phases per round (node visits with queued leaves, then quad tests four at a time), the
 //                     per-ray stack and leaf queue in shared memory.  Finds ALL quad hits of the ray; a ray with more
 //                     than 15 hits is handed to the general kernel of trace.cu (which implements the reference's 16-hit
-//                     chunk restart exactly).  Hits are appended unsorted to hits[ray][16] (t, surfel) = one 128-byte
-//                     line; rays are binned by hit count into per-class lists for the shading kernels.
+//                     chunk restart exactly).  Hits are appended unsorted to hits[ray][16] (t, surfel) = one 128-byte line.
+//   class_*_kernel    stable compaction of the rays into four lists by hit count (0 / 1-4 / 5-8 / 9-15), in pixel order.
 //   shade_fwd_kernel  HIT-parallel: 4, 8 or 16 lanes per ray (by hit count), one hit per lane.  Per-hit evaluation (surfel
 //                     frame, alpha, SH colour) runs in parallel; the front-to-back recurrence T_i = T_{i-1}(1-a_i) is a
-//                     4-step segmented shuffle scan; every accumulated output is one transpose-reduce.
+//                     log2(L)-step segmented shuffle scan; every accumulated output is one transpose-reduce.
 //   shade_bwd_kernel  same layout; the reference's suffix terms (F - F_i)/(1-a_i) come from inclusive scans.  It re-uses
 //                     the forward's hit lists, so the backward pass does no BVH traversal at all.
 //
@@ -71,7 +71,7 @@ __device__ __forceinline__ float safe_inv_f(float d) { return 1.0f / (fabsf(d) >
 // ------------------------------------------------------------------------------------------------------
 // traversal
 // ------------------------------------------------------------------------------------------------------
-// Persistent warps with LANE-level work refill: a lane whose ray has finished immediately takes the next ray from a
+// Persistent warps with GROUP-level work refill: a 4-lane group whose ray has finished takes the next ray from a
 // global cursor (warp-aggregated atomic), so a warp never idles behind its longest ray — reflection rays off a noisy
 // normal map are incoherent and their traversal lengths differ by an order of magnitude.  Ray k maps to pixel
 // (8x4 block k/32, position k%32), so rays fetched together are still neighbours on screen.  Hits are appended
@@ -370,8 +370,8 @@ static int build_class_lists(const FastParams& p, cudaStream_t stream) {
 // hit-parallel shading (L = 4, 8 or 16 lanes per ray, chosen from the ray's hit count)
 // ------------------------------------------------------------------------------------------------------
 // A ray's hits are evaluated one per lane.  With a fixed 16 lanes per ray only ~30 % of the lanes carried a hit (mean
-// 4.9 hits per ray, 30 % of the rays hit nothing), so traverse_kernel sorts the rays into classes by hit count and the
-// shading kernels are instantiated for 4, 8 and 16 lanes per ray; rays without hits are written by a trivial kernel.
+// 4.9 hits per ray, 93 % of the rays have at most 8), so the rays are binned by hit count and the shading kernels are
+// instantiated for 4, 8 and 16 lanes per ray; rays without hits are written by a trivial kernel.
 template <int L>
 __device__ __forceinline__ float seg_scan_mul(float v, int h) {   // inclusive product over the L lanes of a ray
 #pragma unroll
@@ -519,13 +519,8 @@ __device__ __forceinline__ float eval_and_scan(const envgs_trace_args& a, bool v
     if (last < 0) T_final = 1.0f;
 
     if (e.contrib) {   // colour and auxiliaries only where they are used
-#ifdef EXP_NO_SH
-        if (false) {
-            const float* sh = a.shs;
-#else
         if (a.colors_precomp == nullptr) {
             const float* sh = a.shs + (size_t)gidx * a.sh_coeffs * 3;
-#endif
             float3 res = f3(0, 0, 0);
             float gr = 0.0f, gg = 0.0f, gb = 0.0f;
             const bool sh_vec8 = sh_vec4 && ((a.sh_coeffs * 3) % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.shs) & 31) == 0);
@@ -674,9 +669,7 @@ __global__ void __launch_bounds__(256, SFWD_MINBLOCKS) shade_fwd_kernel(const Fa
         int hit_id = 0x7fffffff;
         if (valid) { hit_t = pre_cur.hit.x; hit_id = __float_as_int(pre_cur.hit.y); }
         ray_cur = ray_nxt; ray_nxt = ray_nn; pre_cur = pre_nxt;
-#ifndef EXP_NO_SORT
         seg_bitonic_sort<L>(hit_t, hit_id, h);       // slots [0,cnt) now hold the hits in ascending distance
-#endif
         HitEval e;
         const float T_final = eval_and_scan<L>(a, valid, hit_t, hit_id, ray_o, ray_d, basis, nbasis, sh_vec4, campos, h, e);
 
@@ -693,11 +686,7 @@ __global__ void __launch_bounds__(256, SFWD_MINBLOCKS) shade_fwd_kernel(const Fa
         v[13] = e.w * e.c.x; v[14] = e.w * e.c.y; v[15] = e.w * e.c.z;
         reduce16<L>(v, h);   // v[j], j < VPL: ray-wide sum of component reduce_base(h) + j  (components follow the mid_val layout)
 
-#ifdef EXP_NO_STORE
-        if (live && v[0] == 123.456f) {
-#else
         if (live) {
-#endif
             if (a.training && e.contrib) atomicAdd(&p.o.a_weights[e.gidx], e.w);
             float* mid = p.o.mid_val + ray * 32;
             const int base = reduce_base<L>(h);
@@ -713,9 +702,6 @@ __global__ void __launch_bounds__(256, SFWD_MINBLOCKS) shade_fwd_kernel(const Fa
                 else if (c >= 13) mv = tot + T_final * a.background[c - 13];
                 else mv = tot;
                 mvs[j] = mv;
-#ifdef EXP_NO_OUTS
-                if (mv == 123.456f)
-#endif
                 if (c < 3) __stcs(p.o.out_dist + ray * 3 + c, tot);                 // dist, M1, M2
                 else if (c == 6) __stcs(p.o.out_dpt + ray, mv);
                 else if (c == 7) __stcs(p.o.out_acc + ray, mv);
@@ -925,9 +911,6 @@ __global__ void __launch_bounds__(SBWD_THREADS, SBWD_MINBLOCKS) shade_bwd_kernel
         {
             __syncwarp();
             unsigned int cm = (__ballot_sync(0xffffffffu, e.contrib) >> seg_shift) & seg_mask;
-#ifdef EXP_BWD_NO_SCATTER
-            if (ray == 0x7fffffffu)
-#endif
             while (__any_sync(0xffffffffu, cm != 0u)) {
                 if (cm != 0u) {
                     const int hit = __ffs(cm) - 1;
@@ -971,11 +954,7 @@ __global__ void __launch_bounds__(SBWD_THREADS, SBWD_MINBLOCKS) shade_bwd_kernel
 #pragma unroll
         for (int i = 6; i < 16; i++) v[i] = 0.0f;
         reduce16<L>(v, h);
-#ifdef EXP_BWD_NO_RAYGRAD
-        if (in_list && ray == 0x7fffffffu) {
-#else
         if (in_list) {
-#endif
             const int base = reduce_base<L>(h);
 #pragma unroll
             for (int j = 0; j < VPL; j++) {
