@@ -77,7 +77,7 @@ EXPORTS = [
     "envgs_tracer_destroy", "envgs_tracer_build", "envgs_tracer_bvh_bytes", "envgs_trace_forward",
     "envgs_trace_backward", "envgs_launch_count", "envgs_profile_enable", "envgs_profile_report", "envgs_debug_trace_stats", "envgs_trace_cache_bytes", "envgs_sh_features_forward", "envgs_sh_features_backward",
     "envgs_glue_reflect_forward", "envgs_glue_reflect_backward", "envgs_glue_blend_loss_forward", "envgs_glue_blend_loss_backward",
-    "envgs_adam_step",
+    "envgs_adam_step", "envgs_glue_quad_vertices",
 ]
 
 _lib = None
@@ -136,6 +136,8 @@ def lib() -> C.CDLL:
     L.envgs_glue_blend_loss_forward.argtypes = [C.POINTER(GlueCamera)] + [C.c_void_p] * 4 + [C.c_float] + [C.c_void_p] * 3
     L.envgs_glue_blend_loss_backward.restype = C.c_int
     L.envgs_glue_blend_loss_backward.argtypes = [C.POINTER(GlueCamera)] + [C.c_void_p] * 5 + [C.c_float] + [C.c_void_p] * 6
+    L.envgs_glue_quad_vertices.restype = C.c_int
+    L.envgs_glue_quad_vertices.argtypes = [C.c_int32] + [C.c_void_p] * 5
     L.envgs_adam_step.restype = C.c_int
     L.envgs_adam_step.argtypes = [C.c_uint64] + [C.c_void_p] * 4 + [C.c_int32] + [C.c_float] * 5 + [C.c_int32, C.c_void_p]
     L.envgs_debug_trace_stats.restype = C.c_int

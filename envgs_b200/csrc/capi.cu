@@ -51,6 +51,7 @@ int mark_visible_impl(int P, const float* means3D, const float* viewmatrix, uint
 int trace_forward_impl(Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_out& o, cudaStream_t stream);
 int trace_backward_impl(Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_grads& g, cudaStream_t stream);
 size_t trace_cache_bytes(int H, int W);
+int glue_quad_vertices(int P, const float* means, const float* scales, const float* rots, float* verts, cudaStream_t stream);
 int glue_reflect_forward(const envgs_glue_camera& cam, const float* allmap, float* ref_o, float* ref_d, cudaStream_t stream);
 int glue_reflect_backward(const envgs_glue_camera& cam, const float* allmap, const float* g_ro, const float* g_rd, float* dL_dallmap, cudaStream_t stream);
 int glue_blend_loss_forward(const envgs_glue_camera& cam, const float* image, const float* allmap, const float* env_rgb, const float* target, float lambda_n, float* rgb_out, float* loss2, cudaStream_t stream);
@@ -209,6 +210,11 @@ size_t envgs_trace_cache_bytes(int32_t H, int32_t W) { return trace_cache_bytes(
 static int check_glue_cam(const envgs_glue_camera* c) {
     if (!c || c->H <= 0 || c->W <= 0 || !c->K || !c->R || !c->campos) { set_error("bad glue camera"); return ENVGS_ERR_INVALID; }
     return ENVGS_OK;
+}
+int envgs_glue_quad_vertices(int32_t P, const float* means3D, const float* scales, const float* rotations, float* vertices, void* stream) {
+    if (P < 0 || (P > 0 && (!means3D || !scales || !rotations || !vertices))) { set_error("bad quad_vertices arguments"); return ENVGS_ERR_INVALID; }
+    if ((reinterpret_cast<uintptr_t>(scales) & 7) || (reinterpret_cast<uintptr_t>(rotations) & 15)) { set_error("scales / rotations must be 8 / 16-byte aligned"); return ENVGS_ERR_INVALID; }
+    return glue_quad_vertices(P, means3D, scales, rotations, vertices, (cudaStream_t)stream);
 }
 int envgs_glue_reflect_forward(const envgs_glue_camera* cam, const float* allmap, float* ref_o, float* ref_d, void* stream) {
     int rc = check_glue_cam(cam);

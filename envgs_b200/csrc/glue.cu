@@ -243,4 +243,34 @@ int glue_blend_loss_backward(const envgs_glue_camera& cam, const float* image, c
     return ENVGS_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------
+// surfel -> quad corners at +-3 sigma, reference order [(-,+),(-,-),(+,+),(+,-)] (EVC/utils/optix_utils.py:39-69): the
+// vertex buffer build_acceleration_structure takes, in one launch instead of ~25 element-wise PyTorch ops
+__global__ void __launch_bounds__(256) quad_vertices_kernel(int P, const float* __restrict__ means, const float2* __restrict__ scales,
+                                                            const float4* __restrict__ rots, float* __restrict__ verts) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    float4 q = rots[i];
+    const float inv = 1.0f / sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+    q.x *= inv; q.y *= inv; q.z *= inv; q.w *= inv;
+    const Rot3 R = quat_to_rot(q);
+    const float2 s = scales[i];
+    const float3 mu = ld3(means, i), eu = (3.0f * s.x) * R.c0, ev = (3.0f * s.y) * R.c1;
+    const float su[4] = {-1.0f, -1.0f, 1.0f, 1.0f}, sv[4] = {1.0f, -1.0f, 1.0f, -1.0f};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const float3 v = mu + su[k] * eu + sv[k] * ev;
+        float* o = verts + (size_t)(4 * i + k) * 3;
+        o[0] = v.x; o[1] = v.y; o[2] = v.z;
+    }
+}
+int glue_quad_vertices(int P, const float* means, const float* scales, const float* rots, float* verts, cudaStream_t stream) {
+    if (P <= 0) return ENVGS_OK;
+    ENVGS_TIMED("glue_quad_vertices", stream);
+    quad_vertices_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, means, reinterpret_cast<const float2*>(scales),
+                                                              reinterpret_cast<const float4*>(rots), verts);
+    ENVGS_LAUNCH_CHECK("glue_quad_vertices", false, stream);
+    return ENVGS_OK;
+}
+
 }  // namespace envgs

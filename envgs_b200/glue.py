@@ -101,3 +101,25 @@ def reflect_rays(allmap: torch.Tensor, cam):
 def blend_loss(image: torch.Tensor, allmap: torch.Tensor, env_rgb, target: torch.Tensor, cam, lambda_n: float = 0.04):
     """image (5,H,W), allmap (7,H,W), env rgb (H,W,3) or None, target (H,W,3) -> (rgb (H,W,3), loss scalar, loss parts (2,))."""
     return _BlendLoss.apply(image, allmap, env_rgb, target, cam, lambda_n)
+
+
+_FACES: dict = {}
+
+
+def quad_vertices(means: torch.Tensor, scales: torch.Tensor, rotations: torch.Tensor):
+    """Fused scene.quad_vertices (no gradient, like the reference's GAS build): (4P,3) corners + the cached (2P,3) faces."""
+    P = means.shape[0]
+    m, s, r = (t.detach().to(torch.float32).contiguous() for t in (means, scales, rotations))
+    v = torch.empty((4 * P, 3), dtype=torch.float32, device=means.device)
+    with torch.cuda.device(means.device):
+        _lib.check(_lib.lib().envgs_glue_quad_vertices(P, _lib.ptr(m), _lib.ptr(s), _lib.ptr(r), _lib.ptr(v),
+                                                       torch.cuda.current_stream(means.device).cuda_stream), "envgs_glue_quad_vertices")
+    key = (P, str(means.device))
+    f = _FACES.get(key)
+    if f is None:
+        idx = torch.arange(4 * P, device=means.device).reshape(-1, 4)
+        f = torch.stack([idx[:, :3], idx[:, 1:]], dim=1).reshape(-1, 3).int().contiguous()
+        _FACES.clear()                                   # one face table at a time (P changes only at densification)
+        _FACES[key] = f
+    return v, f
+

@@ -115,7 +115,10 @@ class EnvGSRenderer(nn.Module):
     # ---- environment pass ------------------------------------------------------------------------------------
     def trace_env(self, cam: scene.Camera, ref_o: torch.Tensor, ref_d: torch.Tensor) -> dict:
         with torch.no_grad():
-            v, f = scene.quad_vertices(self.env_means, self.env_scales, self.env_rotations)
+            if self.fused_glue:
+                v, f = glue.quad_vertices(self.env_means, self.env_scales, self.env_rotations)
+            else:
+                v, f = scene.quad_vertices(self.env_means, self.env_scales, self.env_rotations)
             self.tracer.build_acceleration_structure(v, f, rebuild=True)   # every training iteration (optix_utils.py:71-85)
         s = SurfelTracingSettings(cam.H, cam.W, cam.tanfovx, cam.tanfovy, self.env_bg, 1.0, cam.viewmatrix, cam.projmatrix, 3,
                                   cam.campos, False, False, 0, 0.0)

@@ -224,6 +224,11 @@ typedef struct envgs_glue_camera {
     const float* campos;  /* (3,)  device */
 } envgs_glue_camera;
 
+/* Environment surfels -> (4P,3) quad corners at +-3 sigma in the order [(-,+),(-,-),(+,+),(+,-)]: the vertex buffer of
+ * envgs_tracer_build.  Replaces the PyTorch expressions of HardwareRendering.get_disks (EVC/utils/optix_utils.py:39-69);
+ * rotations are normalised first, as there.  No gradient (the reference builds the GAS under no_grad). */
+int envgs_glue_quad_vertices(int32_t P, const float* means3D, const float* scales, const float* rotations, float* vertices, void* stream);
+
 /* allmap (7,H,W) -> reflected rays ref_o, ref_d (H,W,3):  depth = nan_to_num(D/alpha), n = R^T n_view / (|.|+1e-8),
  * d' = d - 2 (d.n) n, o' = campos + depth d */
 int envgs_glue_reflect_forward(const envgs_glue_camera* cam, const float* allmap, float* ref_o, float* ref_d, void* stream);

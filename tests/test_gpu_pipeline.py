@@ -111,3 +111,13 @@ def test_flat_adam_matches_torch_adam(built_lib):
         from envgs_b200 import _lib
         _lib.check(_lib.lib().envgs_adam_step(8, _lib.ptr(flat) + 4, _lib.ptr(grad), _lib.ptr(mine.exp_avg), _lib.ptr(mine.exp_avg_sq), 1,
                                               1e-3, 0.9, 0.999, 1e-15, 1.0, 0, None), "misaligned")
+
+
+def test_fused_quad_vertices_match_pytorch(built_lib):
+    from envgs_b200 import glue
+    env = scene.make_env_set(5003, seed=6, s0=0.05).to("cuda")
+    rots = env.rotations * torch.linspace(0.5, 2.0, env.rotations.shape[0], device="cuda")[:, None]   # unnormalised, like raw parameters
+    v_ref, f_ref = scene.quad_vertices(env.means, env.scales, rots)
+    v, f = glue.quad_vertices(env.means, env.scales, rots)
+    assert torch.equal(f, f_ref)
+    assert float((v - v_ref).abs().max()) <= 2e-6 * float(v_ref.abs().max())
