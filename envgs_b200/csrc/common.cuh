@@ -185,6 +185,19 @@ __device__ __forceinline__ void sh_dir_grad(int deg, float3 d, const float* sh, 
 #undef SHV
 }
 
+// Per-(pixel, surfel) / per-hit reciprocal and exponential of the render and shading kernels: the 1-instruction MUFU forms
+// (rcp.approx / ex2.approx, <= 2 ulp; the arguments are bounded: alpha >= 1/255 keeps the exponent in [-5.6, 0]), used
+// identically by the forward and the backward kernels so both take the same alpha / termination decisions.  The reference is
+// built without -use_fast_math; the difference is far inside the 1e-4 / 1e-3 parity tolerance (golden tests run on this form).
+// -DENVGS_IEEE_MATH selects IEEE division and expf instead (5-9 % slower render kernels).
+#ifndef ENVGS_IEEE_MATH
+__device__ __forceinline__ float px_rcp(float x) { return __fdividef(1.0f, x); }
+__device__ __forceinline__ float px_exp(float x) { return __expf(x); }
+#else
+__device__ __forceinline__ float px_rcp(float x) { return 1.0f / x; }
+__device__ __forceinline__ float px_exp(float x) { return expf(x); }
+#endif
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

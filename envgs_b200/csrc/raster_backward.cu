@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(256, RBWD_MINBLOCKS) render_bwd_kernel(
                 float3 l = pyf * Tw - Tv;
                 float3 p = cross(k, l);
                 if (p.z != 0.0f) {
-                    const float rz = 1.0f / p.z;                 // same reciprocal form as the forward kernel
+                    const float rz = px_rcp(p.z);                // same reciprocal form as the forward kernel
                     float sx = p.x * rz, sy = p.y * rz;
                     float rho3d = sx * sx + sy * sy;
                     float dx = r2.y - pxf, dy = r2.z - pyf;
@@ -155,12 +155,12 @@ __global__ void __launch_bounds__(256, RBWD_MINBLOCKS) render_bwd_kernel(
                     float power = -0.5f * rho;
                     if (c_d >= NEAR_N && power <= 0.0f) {
                         const float opa = r2.w;
-                        const float G = expf(power);
+                        const float G = px_exp(power);
                         const float alpha = fminf(ALPHA_MAX, opa * G);
                         if (alpha >= ALPHA_MIN) {
                             contrib = true;
                             const float4 r3 = s_r3[j];
-                            const float r1ma = 1.0f / (1.0f - alpha);
+                            const float r1ma = px_rcp(1.0f - alpha);
                             T = T * r1ma;
                             const float w = alpha * T;
                             float dL_dalpha = 0.0f;
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(256, RBWD_MINBLOCKS) render_bwd_kernel(
                                 g[ch] = w * dL_dpixel[ch];
                             }
                             float dL_dz = 0.0f, dL_dweight = 0.0f;
-                            const float rcd = 1.0f / c_d;
+                            const float rcd = px_rcp(c_d);
                             const float m_d = FAR_N / (FAR_N - NEAR_N) * (1.0f - NEAR_N * rcd);
                             const float dmd_dd = (FAR_N * NEAR_N) / (FAR_N - NEAR_N) * rcd * rcd;
                             if (pos == median_contributor) dL_dz += dL_dmedian_depth;

@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(
                 float3 l = pyf * Tw - Tv;
                 float3 p = cross(k, l);
                 if (p.z != 0.0f) {
-                    const float rz = 1.0f / p.z;                 // one IEEE reciprocal instead of two divisions (<= 1 ulp apart)
+                    const float rz = px_rcp(p.z);                // one reciprocal instead of two divisions (<= 1 ulp apart)
                     float sx = p.x * rz, sy = p.y * rz;
                     float rho3d = sx * sx + sy * sy;
                     float dx = r2.y - pxf, dy = r2.z - pyf;
@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(
                     float depth = (rho3d <= rho2d) ? (sx * Tw.x + sy * Tw.y) + Tw.z : Tw.z;
                     float power = -0.5f * rho;
                     if (depth >= NEAR_N && power <= 0.0f) {
-                        float alpha = fminf(ALPHA_MAX, r2.w * expf(power));
+                        float alpha = fminf(ALPHA_MAX, r2.w * px_exp(power));
                         if (alpha >= ALPHA_MIN) {
                             float test_T = T * (1.0f - alpha);
                             if (test_T < T_STOP) {
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(
                                 w = alpha * T;
                                 const float4 r3 = s_r3[j];
                                 float A = 1.0f - T;
-                                float m = FAR_N / (FAR_N - NEAR_N) * (1.0f - NEAR_N / depth);
+                                float m = FAR_N / (FAR_N - NEAR_N) * (1.0f - NEAR_N * px_rcp(depth));
                                 distortion += (m * m * A + M2 - 2.0f * m * M1) * w;
                                 Dacc += depth * w;
                                 M1 += m * w;

@@ -486,7 +486,7 @@ __device__ __forceinline__ float eval_and_scan(const envgs_trace_args& a, bool v
         const float Tx = dot(e.tu, e.mu), Ty = dot(e.tv, e.mu);
         const float u1 = e.tu.x * e.xyz.x + e.tu.y * e.xyz.y + e.tu.z * e.xyz.z + (-Tx);
         const float v1 = e.tv.x * e.xyz.x + e.tv.y * e.xyz.y + e.tv.z * e.xyz.z + (-Ty);
-        e.uv = make_float2(u1 / e.scale.x, v1 / e.scale.y);
+        e.uv = make_float2(u1 * px_rcp(e.scale.x), v1 * px_rcp(e.scale.y));
         const float rho3d = e.uv.x * e.uv.x + e.uv.y * e.uv.y;
         const float cosv = -sum3((e.mu - campos) * nr);
         if (cosv == 0.0f) cand = false;
@@ -497,7 +497,7 @@ __device__ __forceinline__ float eval_and_scan(const envgs_trace_args& a, bool v
         const float power = -0.5f * rho3d;
         if (power > 0.0f) cand = false;
         e.opac = a.opacities[gidx];
-        e.G = expf(power);
+        e.G = px_exp(power);
         e.alpha = fminf(0.99f, e.opac * e.G);
         if (e.alpha < 1.0f / 255.0f) cand = false;
     }
@@ -674,7 +674,7 @@ __global__ void __launch_bounds__(256, SFWD_MINBLOCKS) shade_fwd_kernel(const Fa
         const float T_final = eval_and_scan<L>(a, valid, hit_t, hit_id, ray_o, ray_d, basis, nbasis, sh_vec4, campos, h, e);
 
         // distortion bookkeeping needs exclusive prefix sums of w*m and w*m^2 (forward.cu:405-409)
-        const float m = FAR_N / (FAR_N - NEAR_N) * (1.0f - NEAR_N / e.cmd);
+        const float m = FAR_N / (FAR_N - NEAR_N) * (1.0f - NEAR_N * px_rcp(e.cmd));
         const float wm = e.w * m, wmm = e.w * m * m;
         const float M1_ex = seg_scan_add<L>(wm, h) - wm, M2_ex = seg_scan_add<L>(wmm, h) - wmm;
         float v[16];
@@ -847,7 +847,7 @@ __global__ void __launch_bounds__(SBWD_THREADS, SBWD_MINBLOCKS) shade_bwd_kernel
         if (e.contrib) {
             const int gidx = e.gidx;
             const float alpha = e.alpha, T_prev = e.T_prev, w = e.w, G = e.G, cmd = e.cmd;
-            const float r1ma = 1.0f / (1.0f - alpha);
+            const float r1ma = px_rcp(1.0f - alpha);
             const float cc[3] = {e.c.x, e.c.y, e.c.z}, Cc[3] = {Cx, Cy, Cz}, O[2] = {O0, O1};
             float dL_dalpha = 0.0f;
             float dL_dcolor[3];
@@ -873,7 +873,7 @@ __global__ void __launch_bounds__(SBWD_THREADS, SBWD_MINBLOCKS) shade_bwd_kernel
             const float dL_dopac = dL_dalpha * G;   // straight-through cap (backward.cu:801-806)
 
             // compute_transmat_uv_backward (backward.cu:233-335), plane form t = m.(mu-o)/(m.d), m = t_u x t_v
-            const float isx = 1.0f / e.scale.x, isy = 1.0f / e.scale.y;
+            const float isx = px_rcp(e.scale.x), isy = px_rcp(e.scale.y);
             const float2 dL_duv = make_float2(dL_dG * -G * e.uv.x, dL_dG * -G * e.uv.y);
             const float3 xm = e.xyz - e.mu;
             float3 dR0 = (dL_duv.x * isx) * xm;
@@ -884,7 +884,7 @@ __global__ void __launch_bounds__(SBWD_THREADS, SBWD_MINBLOCKS) shade_bwd_kernel
             const float3 dL_dxyz = (dL_duv.x * isx) * e.tu + (dL_duv.y * isy) * e.tv;
             const float dL_dd = dL_dD + dot(dL_dxyz, ray_d);
             const float3 mvec = cross(e.tu, e.tv);
-            const float iqd = 1.0f / dot(mvec, ray_d);
+            const float iqd = px_rcp(dot(mvec, ray_d));
             const float3 cvec = e.mu - ray_o;
             const float pn = dot(mvec, cvec);
             const float3 dt_dm = (cvec - (pn * iqd) * ray_d) * iqd;
