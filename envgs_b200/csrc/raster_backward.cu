@@ -11,7 +11,10 @@
 
 namespace envgs {
 
-constexpr int BB = 128;          // surfels staged per batch (CTA = 256 threads; keeps static smem < 48 KB for C = 7)
+#ifndef RBWD_BATCH
+#define RBWD_BATCH 256
+#endif
+constexpr int BB = RBWD_BATCH;   // surfels staged per batch (<= CTA size 256)
 constexpr int NG_FIX = 15;       // reduced values besides colour: normal(3) opacity(1) dT(9) dmean2D(2)
 
 #ifndef RBWD_MINBLOCKS
