@@ -594,7 +594,7 @@ __device__ __forceinline__ float eval_and_scan(const envgs_trace_args& a, bool v
 }
 
 // rays without any hit: background colour, everything else zero (forward.cu:444-449 with an empty loop)
-__global__ void __launch_bounds__(256) shade_empty_kernel(const FastParams p) {
+__device__ __forceinline__ void shade_empty_body(const FastParams& p) {
     const unsigned int n = p.class_count[0];
     const envgs_trace_args& a = p.a;
     for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
@@ -616,10 +616,10 @@ __global__ void __launch_bounds__(256) shade_empty_kernel(const FastParams p) {
 }
 
 #ifndef SFWD_MINBLOCKS
-#define SFWD_MINBLOCKS 5
+#define SFWD_MINBLOCKS 4
 #endif
 template <int L>
-__global__ void __launch_bounds__(256, SFWD_MINBLOCKS) shade_fwd_kernel(const FastParams p, int cls) {
+__device__ __forceinline__ void shade_fwd_body(const FastParams& p, int cls) {
     constexpr int RPW = 32 / L;              // rays per warp
     constexpr int VPL = 16 / L;              // reduced components per lane
     const envgs_trace_args& a = p.a;
@@ -725,6 +725,15 @@ __global__ void __launch_bounds__(256, SFWD_MINBLOCKS) shade_fwd_kernel(const Fa
     }
 }
 
+// ONE launch for all hit classes: a warp that runs out of 4-lane rays moves straight on to the 8- and 16-lane ones, so there
+// are no idle tails and launch gaps between the classes (three short kernels back to back left the GPU partly idle 3 times).
+__global__ void __launch_bounds__(256, SFWD_MINBLOCKS) shade_fwd_kernel(const FastParams p) {
+    shade_empty_body(p);
+    shade_fwd_body<4>(p, 1);
+    shade_fwd_body<8>(p, 2);
+    shade_fwd_body<16>(p, 3);
+}
+
 // d basis_k / d(x,y,z) of the SH polynomials (RAST backward.cu:58-122 collects the same terms per colour channel)
 __device__ __forceinline__ float3 sh_basis_grad(int k, float3 d) {
     const float x = d.x, y = d.y, z = d.z;
@@ -758,13 +767,11 @@ constexpr int GR_STRIDE = 20;   // floats per staged hit-gradient record
 #define SBWD_MINBLOCKS 2
 #endif
 template <int L>
-__global__ void __launch_bounds__(SBWD_THREADS, SBWD_MINBLOCKS) shade_bwd_kernel(const FastParams p, int cls) {
+__device__ __forceinline__ void shade_bwd_body(const FastParams& p, int cls, float* s_rec, float* s_basis) {
     // per-hit gradient records staged in shared memory so the 61 atomics of a contributing hit are issued by all lanes of
-    // the ray instead of one lane after another
+    // the ray instead of one lane after another (s_rec: one record per thread = per hit slot; s_basis: 8 x 16 floats per warp)
     constexpr int RPW = 32 / L;
     constexpr int VPL = 16 / L;
-    __shared__ float s_rec[SBWD_THREADS * GR_STRIDE];    // one record per thread (= per hit slot)
-    __shared__ float s_basis[(SBWD_THREADS / L) * 16];
     const envgs_trace_args& a = p.a;
     const envgs_trace_grads& g = p.g;
     const int lane = threadIdx.x & 31;
@@ -806,7 +813,7 @@ __global__ void __launch_bounds__(SBWD_THREADS, SBWD_MINBLOCKS) shade_bwd_kernel
         float basis[16];
         const float3 dirn = normalize3(ray_d);
         if (use_sh) sh_basis(a.sh_degree, dirn, basis);
-        float* sb = s_basis + ray_slot * 16;          // the scatter phase reads the basis from shared memory: written now so
+        float* sb = s_basis + (threadIdx.x >> 5) * 128 + (lane / L) * 16;   // the scatter phase reads the basis from shared memory: written now so
         if (use_sh && h == 0) {                        // the 16 registers die after the colour evaluation
 #pragma unroll
             for (int k = 0; k < 16; k++) sb[k] = k < nbasis ? basis[k] : 0.0f;
@@ -966,6 +973,14 @@ __global__ void __launch_bounds__(SBWD_THREADS, SBWD_MINBLOCKS) shade_bwd_kernel
     }
 }
 
+// (one launch per class here: the merged form of the forward kernel spilled at 128 registers and ran 4 % slower)
+template <int L>
+__global__ void __launch_bounds__(SBWD_THREADS, SBWD_MINBLOCKS) shade_bwd_kernel(const FastParams p, int cls) {
+    __shared__ float s_rec[SBWD_THREADS * GR_STRIDE];
+    __shared__ float s_basis[(SBWD_THREADS / 32) * 128];
+    shade_bwd_body<L>(p, cls, s_rec, s_basis);
+}
+
 // ------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------
@@ -1016,28 +1031,27 @@ int trace_forward_fast(Lbvh& bvh, unsigned int* counter, unsigned long long* sta
         else traverse_kernel<false><<<blocks, TF_THREADS, 0, stream>>>(p);
         ENVGS_LAUNCH_CHECK("trace_traverse", false, stream);
     }
+    // rays whose first chunk was full: the reference's multi-chunk loop, run by the general kernel on the device-side list.  It is
+    // forked BEFORE the (tiny) class-list kernels so that its few CTAs are resident when the persistent shading kernel, which
+    // fills every SM for its whole duration, starts.
+    ENVGS_CUDA_TRY(cudaEventRecord(side.fork, stream));
+    ENVGS_CUDA_TRY(cudaStreamWaitEvent(side.stream, side.fork, 0));
+    int rc = launch_trace(false, bvh, counter, stats, a, &o, nullptr, p.overflow_list, p.overflow_count, side.stream);
+    if (rc != ENVGS_OK) return rc;
     {
         ENVGS_TIMED("trace_class_lists", stream);
         int rcl = build_class_lists(p, stream);
         if (rcl != ENVGS_OK) return rcl;
     }
-    // rays whose first chunk was full: the reference's multi-chunk loop, run by the general kernel on the device-side list
-    ENVGS_CUDA_TRY(cudaEventRecord(side.fork, stream));
-    ENVGS_CUDA_TRY(cudaStreamWaitEvent(side.stream, side.fork, 0));
-    int rc = launch_trace(false, bvh, counter, stats, a, &o, nullptr, p.overflow_list, p.overflow_count, side.stream);
-    if (rc != ENVGS_OK) return rc;
     ENVGS_CUDA_TRY(cudaEventRecord(side.join, side.stream));
     {
         ENVGS_TIMED("trace_shade_fwd", stream);
-        const int sblocks = sm_count * 8;
-        shade_empty_kernel<<<sblocks, 256, 0, stream>>>(p);
-        ENVGS_LAUNCH_CHECK("trace_shade_empty", false, stream);
-        shade_fwd_kernel<4><<<sblocks, 256, 0, stream>>>(p, 1);
-        ENVGS_LAUNCH_CHECK("trace_shade_fwd4", false, stream);
-        shade_fwd_kernel<8><<<sblocks, 256, 0, stream>>>(p, 2);
-        ENVGS_LAUNCH_CHECK("trace_shade_fwd8", false, stream);
-        shade_fwd_kernel<16><<<sblocks, 256, 0, stream>>>(p, 3);
-        ENVGS_LAUNCH_CHECK("trace_shade_fwd16", false, stream);
+        // statically strided items: several CTA "waves" per SM let late waves fill the holes early finishers leave
+        static int per_sm = 0;
+        if (per_sm == 0) { const char* e = getenv("ENVGS_SHADE_GRID"); per_sm = e ? atoi(e) : 64; if (per_sm < 1) per_sm = 1; }
+        const int sblocks = sm_count * per_sm;
+        shade_fwd_kernel<<<sblocks, 256, 0, stream>>>(p);
+        ENVGS_LAUNCH_CHECK("trace_shade_fwd", false, stream);
     }
     ENVGS_CUDA_TRY(cudaStreamWaitEvent(stream, side.join, 0));
     return ENVGS_OK;
@@ -1062,7 +1076,9 @@ int trace_backward_fast(Lbvh& bvh, unsigned int* counter, unsigned long long* st
     ENVGS_CUDA_TRY(cudaEventRecord(side.join, side.stream));
     {
         ENVGS_TIMED("trace_shade_bwd", stream);
-        const int sblocks = sm_count * SBWD_MINBLOCKS;   // persistent grid-stride kernels: exactly the resident CTAs
+        static int per_sm_b = 0;   // CTAs per SM launched (items are statically strided; see trace_forward_fast)
+        if (per_sm_b == 0) { const char* e = getenv("ENVGS_SHADE_GRID_BWD"); per_sm_b = e ? atoi(e) : SBWD_MINBLOCKS; if (per_sm_b < 1) per_sm_b = 1; }
+        const int sblocks = sm_count * per_sm_b;
         shade_bwd_kernel<4><<<sblocks, SBWD_THREADS, 0, stream>>>(p, 1);
         ENVGS_LAUNCH_CHECK("trace_shade_bwd4", false, stream);
         shade_bwd_kernel<8><<<sblocks, SBWD_THREADS, 0, stream>>>(p, 2);
