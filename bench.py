@@ -54,7 +54,7 @@ class ClockSampler:
     """SM clock + throttle reasons sampled DURING the timed region through NVML (a few microseconds per query; an
     `nvidia-smi -lms` loop holds driver locks long enough to stall this launch-heavy step)."""
 
-    def __init__(self, gpu_index: int, period_s: float = 0.2):
+    def __init__(self, gpu_index: int, period_s: float = 0.05):
         self.gpu, self.period = gpu_index, period_s
         self.samples, self.reasons, self.max_clock = [], set(), None
         self._stop = threading.Event()
