@@ -144,3 +144,19 @@ def test_view_parallel_gradient_allreduce_gloo_world2():
     for rank, flat_grad, is_view in res:
         assert is_view                                        # parameter grads are views into the single flat buffer
         assert torch.allclose(flat_grad, expect, rtol=1e-5, atol=1e-5)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU oracle arm) prints one JSON line with the keys the driver reads and never touches CUDA."""
+    import json, subprocess, sys
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "tiny", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.strip().splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["value"] > 0 and d["unit"] == "Mpix/s" and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0 and "workload" in d["config"]
