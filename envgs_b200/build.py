@@ -46,7 +46,7 @@ def _digest() -> str:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ_DIR, exist_ok=True)
-    stamp = os.path.join(OBJ_DIR, "stamp")
+    stamp = LIB_PATH + ".stamp"   # next to the library: travels with it to the GPU box (the object directory does not)
     digest = _digest()
     if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp) and open(stamp).read() == digest:
         return LIB_PATH
