@@ -185,17 +185,22 @@ __device__ __forceinline__ void sh_dir_grad(int deg, float3 d, const float* sh, 
 #undef SHV
 }
 
-// Per-(pixel, surfel) / per-hit reciprocal and exponential of the render and shading kernels: the 1-instruction MUFU forms
-// (rcp.approx / ex2.approx, <= 2 ulp; the arguments are bounded: alpha >= 1/255 keeps the exponent in [-5.6, 0]), used
-// identically by the forward and the backward kernels so both take the same alpha / termination decisions.  The reference is
-// built without -use_fast_math; the difference is far inside the 1e-4 / 1e-3 parity tolerance (golden tests run on this form).
-// -DENVGS_IEEE_MATH selects IEEE division and expf instead (5-9 % slower render kernels).
-#ifndef ENVGS_IEEE_MATH
+// Per-(pixel, surfel) / per-hit division and exponential of the render and shading kernels.
+// DEFAULT: the reference's own IEEE forms (`a / b`, `expf`; it is built without -use_fast_math).  Together with the
+// reference-ordered per-surfel preprocess (glm_order.cuh, compute_aabb) this makes the rasterizer's forward outputs agree
+// with the reference build to 2e-7 and its gradients to 4e-7 relative L2 at 1 M surfels / 1080p
+// (profiles/round2_parity_experiments.md), because every alpha >= 1/255, T < 1e-4, T > 0.5 and rho3d <= rho2d decision is
+// then taken on identical bits.  Forward and backward kernels use the same helpers, so they always agree with each other.
+// -DENVGS_FAST_MATH selects the 1-instruction MUFU forms (rcp.approx / ex2.approx, <= 2 ulp): render kernels 14-17 % faster,
+// gradients still within 8e-5 relative L2, but ~3 of 2 M pixels flip an alpha >= 1/255 decision (colour error up to 1e-3).
+#ifdef ENVGS_FAST_MATH
 __device__ __forceinline__ float px_rcp(float x) { return __fdividef(1.0f, x); }
 __device__ __forceinline__ float px_exp(float x) { return __expf(x); }
+__device__ __forceinline__ float px_div(float a, float b, float rb) { return a * rb; }   // rb = px_rcp(b)
 #else
 __device__ __forceinline__ float px_rcp(float x) { return 1.0f / x; }
 __device__ __forceinline__ float px_exp(float x) { return expf(x); }
+__device__ __forceinline__ float px_div(float a, float b, float) { return a / b; }       // the reference's own a / b
 #endif
 
 __device__ __forceinline__ float warp_sum(float v) {

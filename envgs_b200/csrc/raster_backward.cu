@@ -8,6 +8,7 @@
 //   preprocess_bwd_kernel  per surfel chain rule dL/dT, dL/dnormal, dL/dmean2D -> mean/scale/quat (+SH)
 //                          (backward.cu:443-630), including the densification-signal overwrite (:626-629).
 #include "raster_state.cuh"
+#include "glm_order.cuh"
 
 namespace envgs {
 
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(256, RBWD_MINBLOCKS) render_bwd_kernel(
                 float3 p = cross(k, l);
                 if (p.z != 0.0f) {
                     const float rz = px_rcp(p.z);                // same reciprocal form as the forward kernel
-                    float sx = p.x * rz, sy = p.y * rz;
+                    float sx = px_div(p.x, p.z, rz), sy = px_div(p.y, p.z, rz);
                     float rho3d = sx * sx + sy * sy;
                     float dx = r2.y - pxf, dy = r2.z - pyf;
                     float rho2d = FILTER_INV_SQUARE * (dx * dx + dy * dy);
@@ -266,7 +267,7 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
     float2 scale = make_float2(0, 0);
     float4 rot = make_float4(1, 0, 0, 0);
     Rot3 R;
-    float Q[3][4];   // Q = N * PV (3x4)
+    GMat<3, 4> Pm;   // P = world2ndc * ndc2pix (backward.cu:496), reference GLM operation order (glm_order.cuh)
     const bool precomp = (scales == nullptr);
     if (precomp) {
         const float* t = transMat_precomp + 9 * (size_t)idx;
@@ -275,25 +276,21 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
         scale = scales[idx];
         rot = rotations[idx];
         R = quat_to_rot(rot);
-        float3 L0 = R.c0 * scale.x, L1 = R.c1 * scale.y;   // scale_modifier ignored here (backward.cu:481)
-        float hw = float(W) / 2.0f, cw = float(W - 1) / 2.0f, hh = float(H) / 2.0f, chh = float(H - 1) / 2.0f;
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-            float pv0 = pm[4 * r + 0], pv1 = pm[4 * r + 1], pv3 = pm[4 * r + 3];   // PV[i][r] = pm[4*r + i]
-            Q[0][r] = pv0 * hw + pv3 * cw;
-            Q[1][r] = pv1 * hh + pv3 * chh;
-            Q[2][r] = pv3;
-        }
-        // T rows = Q * S
-        float4 s0 = make_float4(L0.x, L0.y, L0.z, 0.0f), s1 = make_float4(L1.x, L1.y, L1.z, 0.0f),
-               s2 = make_float4(p_orig.x, p_orig.y, p_orig.z, 1.0f);
-        auto row = [&](int i) {
-            return f3(Q[i][0] * s0.x + Q[i][1] * s0.y + Q[i][2] * s0.z + Q[i][3] * s0.w,
-                      Q[i][0] * s1.x + Q[i][1] * s1.y + Q[i][2] * s1.z + Q[i][3] * s1.w,
-                      Q[i][0] * s2.x + Q[i][1] * s2.y + Q[i][2] * s2.z + Q[i][3] * s2.w);
-        };
-        Tu = row(0); Tv = row(1); Tw = row(2);
-        normal = xform_vec_4x3(R.c2, viewmatrix);
+        GMat<3, 3> Rm = {{{R.c0.x, R.c0.y, R.c0.z}, {R.c1.x, R.c1.y, R.c1.z}, {R.c2.x, R.c2.y, R.c2.z}}};
+        GMat<3, 3> S = {{{1.0f * scale.x, 0.0f, 0.0f}, {0.0f, 1.0f * scale.y, 0.0f}, {0.0f, 0.0f, 1.0f}}};   // scale_modifier ignored (backward.cu:481)
+        GMat<3, 3> L = gmul<3, 3, 3>(Rm, S);
+        GMat<3, 4> M = {{{L.v[0][0], L.v[0][1], L.v[0][2], 0.0f}, {L.v[1][0], L.v[1][1], L.v[1][2], 0.0f},
+                         {p_orig.x, p_orig.y, p_orig.z, 1.0f}}};
+        GMat<4, 4> world2ndc = {{{pm[0], pm[4], pm[8], pm[12]}, {pm[1], pm[5], pm[9], pm[13]}, {pm[2], pm[6], pm[10], pm[14]},
+                                 {pm[3], pm[7], pm[11], pm[15]}}};
+        GMat<3, 4> ndc2pix = {{{float(W) / 2.0f, 0.0f, 0.0f, float(W - 1) / 2.0f},
+                               {0.0f, float(H) / 2.0f, 0.0f, float(H - 1) / 2.0f}, {0.0f, 0.0f, 0.0f, 1.0f}}};
+        Pm = gmul<4, 4, 3>(world2ndc, ndc2pix);
+        GMat<3, 3> T = gmul<4, 3, 3>(gtranspose(M), Pm);
+        Tu = f3(T.v[0][0], T.v[0][1], T.v[0][2]);
+        Tv = f3(T.v[1][0], T.v[1][1], T.v[1][2]);
+        Tw = f3(T.v[2][0], T.v[2][1], T.v[2][2]);
+        normal = xform_vec_4x3(f3(L.v[2][0], L.v[2][1], L.v[2][2]), viewmatrix);
     }
 
     const float m2x = dL_dmean2Ds[3 * (size_t)idx + 0], m2y = dL_dmean2Ds[3 * (size_t)idx + 1];
@@ -305,7 +302,7 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
         float3 dT1 = m2y * f_vec * Tw;
         float3 dT3 = m2x * f_vec * Tu + m2y * f_vec * Tv;
         float3 dL_df = m2x * Tu * Tw + m2y * Tv * Tw;
-        float dL_dd = dot(dL_df, f_vec) * (-1.0f / d);
+        float dL_dd = (float)((double)dot(dL_df, f_vec) * (-1.0 / (double)d));   // the reference's `-1.0 / d` is a double expression (backward.cu:525)
         float3 dd_dT3 = t_vec * Tw * 2.0f;
         dT3 += dL_dd * dd_dT3;
         gTu += dT0; gTv += dT1; gTw += dT3;
@@ -316,14 +313,12 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
     }
 
     if (!precomp) {
-        // dL/dS = Q^T * [gTu; gTv; gTw]  (4x3); columns: d/dL0, d/dL1, d/d(p,1)
+        // dL_dM = P * transpose(dL_dT) (backward.cu:547): columns d/dL0, d/dL1, d/d(p,1)
+        GMat<3, 3> dLdT = {{{gTu.x, gTu.y, gTu.z}, {gTv.x, gTv.y, gTv.z}, {gTw.x, gTw.y, gTw.z}}};
+        GMat<3, 4> dM = gmul<3, 4, 3>(Pm, gtranspose(dLdT));
         float dS[4][3];
 #pragma unroll
-        for (int r = 0; r < 4; r++) {
-            dS[r][0] = Q[0][r] * gTu.x + Q[1][r] * gTv.x + Q[2][r] * gTw.x;
-            dS[r][1] = Q[0][r] * gTu.y + Q[1][r] * gTv.y + Q[2][r] * gTw.y;
-            dS[r][2] = Q[0][r] * gTu.z + Q[1][r] * gTv.z + Q[2][r] * gTw.z;
-        }
+        for (int r = 0; r < 4; r++) { dS[r][0] = dM.v[0][r]; dS[r][1] = dM.v[1][r]; dS[r][2] = dM.v[2][r]; }
         float3 dL_dtn = xform_vec_4x3_T(ld3(dL_dnormal3Ds, idx), viewmatrix);
         float3 p_view = xform_point_4x3(p_orig, viewmatrix);
         float cosv = -sum3(p_view * normal);
@@ -367,8 +362,10 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(
 
     // densification signal (backward.cu:626-629): depth = forward transMat[8] = Tw.z of the stored record
     float depth = precomp ? transMat_precomp[9 * (size_t)idx + 8] : rec[4 * (size_t)idx + 2].x;
-    dL_dmean2Ds[3 * (size_t)idx + 0] = dT_render2 * depth * 0.5f * float(W);
-    dL_dmean2Ds[3 * (size_t)idx + 1] = dT_render5 * depth * 0.5f * float(H);
+    // with a precomputed transMat the reference has already folded the centre term into dL_dTs at this point (:532-543)
+    const bool folded = precomp && (m2x != 0.0f || m2y != 0.0f);
+    dL_dmean2Ds[3 * (size_t)idx + 0] = (folded ? gTu.z : dT_render2) * depth * 0.5f * float(W);
+    dL_dmean2Ds[3 * (size_t)idx + 1] = (folded ? gTv.z : dT_render5) * depth * 0.5f * float(H);
 }
 
 template <int C>

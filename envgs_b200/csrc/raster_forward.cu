@@ -10,6 +10,7 @@
 //   render_fwd_kernel  -> per-pixel front-to-back compositing (forward.cu:256-445)
 #include <cub/cub.cuh>
 #include "raster_state.cuh"
+#include "glm_order.cuh"
 
 namespace envgs {
 
@@ -73,39 +74,65 @@ size_t BinningState::carve(char* base, int N, BinningState* s, size_t sort_bytes
 // preprocess
 // ------------------------------------------------------------------------------------------------------
 
-// 3x3 homography rows (Tu,Tv,Tw) = rows of N * PV * S  (forward.cu:75-115)
+// 3x3 homography rows (Tu,Tv,Tw) = rows of N * PV * S  (forward.cu:75-115), evaluated in the reference's
+// GLM operation order `T = transpose(splat2world) * world2ndc * ndc2pix` (see glm_order.cuh for why the order matters).
 __device__ __forceinline__ void compute_transmat(float3 p, float2 scale, float mod, float4 rot, const float* pm,
                                                  const float* vm, int W, int H, float3& Tu, float3& Tv, float3& Tw,
                                                  float3& normal) {
-    Rot3 R = quat_to_rot(rot);
-    float3 L0 = R.c0 * (mod * scale.x);
-    float3 L1 = R.c1 * (mod * scale.y);
-    // A = PV * S, PV[r][c] = pm[4*c + r]
-    float A[4][3];
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-        A[r][0] = L0.x * pm[r] + L0.y * pm[4 + r] + L0.z * pm[8 + r];
-        A[r][1] = L1.x * pm[r] + L1.y * pm[4 + r] + L1.z * pm[8 + r];
-        A[r][2] = p.x * pm[r] + p.y * pm[4 + r] + p.z * pm[8 + r] + pm[12 + r];
-    }
-    float hw = float(W) / 2.0f, cw = float(W - 1) / 2.0f, hh = float(H) / 2.0f, ch = float(H - 1) / 2.0f;
-    Tu = f3(A[0][0] * hw + A[3][0] * cw, A[0][1] * hw + A[3][1] * cw, A[0][2] * hw + A[3][2] * cw);
-    Tv = f3(A[1][0] * hh + A[3][0] * ch, A[1][1] * hh + A[3][1] * ch, A[1][2] * hh + A[3][2] * ch);
-    Tw = f3(A[3][0], A[3][1], A[3][2]);
-    normal = xform_vec_4x3(R.c2, vm);
+    Rot3 Rq = quat_to_rot(rot);
+    GMat<3, 3> R = {{{Rq.c0.x, Rq.c0.y, Rq.c0.z}, {Rq.c1.x, Rq.c1.y, Rq.c1.z}, {Rq.c2.x, Rq.c2.y, Rq.c2.z}}};
+    GMat<3, 3> S = {{{mod * scale.x, 0.0f, 0.0f}, {0.0f, mod * scale.y, 0.0f}, {0.0f, 0.0f, 1.0f}}};   // scale_to_mat
+    GMat<3, 3> L = gmul<3, 3, 3>(R, S);
+    GMat<3, 4> splat2world = {{{L.v[0][0], L.v[0][1], L.v[0][2], 0.0f}, {L.v[1][0], L.v[1][1], L.v[1][2], 0.0f}, {p.x, p.y, p.z, 1.0f}}};
+    GMat<4, 4> world2ndc = {{{pm[0], pm[4], pm[8], pm[12]}, {pm[1], pm[5], pm[9], pm[13]}, {pm[2], pm[6], pm[10], pm[14]},
+                             {pm[3], pm[7], pm[11], pm[15]}}};
+    GMat<3, 4> ndc2pix = {{{float(W) / 2.0f, 0.0f, 0.0f, float(W - 1) / 2.0f}, {0.0f, float(H) / 2.0f, 0.0f, float(H - 1) / 2.0f},
+                           {0.0f, 0.0f, 0.0f, 1.0f}}};
+    GMat<3, 3> T = gmul<4, 3, 3>(gmul<4, 3, 4>(gtranspose(splat2world), world2ndc), ndc2pix);
+    Tu = f3(T.v[0][0], T.v[0][1], T.v[0][2]);
+    Tv = f3(T.v[1][0], T.v[1][1], T.v[1][2]);
+    Tw = f3(T.v[2][0], T.v[2][1], T.v[2][2]);
+    normal = xform_vec_4x3(f3(L.v[2][0], L.v[2][1], L.v[2][2]), vm);
 }
 
-// centre + half extent of the screen-space conic {u^2+v^2 <= cutoff^2} (forward.cu:119-145)
+// centre + half extent of the screen-space conic {u^2+v^2 <= cutoff^2} (forward.cu:119-145).
+// Written with explicit round-to-nearest intrinsics in the operation order the reference build executes (read off the SASS
+// of its preprocessCUDA<5>, nvcc 12.9 -O3 sm_100a): which product of each three-term dot stays a separately rounded
+// multiply and which ones are fused is otherwise at the mercy of common-subexpression sharing with neighbouring code, and
+// a 1-ulp change of d moves the centre on ~20 % of the surfels and the integer radius on ~0.15 % of them.
+//   d      = fma(-Tw.z, Tw.z, fma(Tw.x^2, 9, (Tw.y^2) * 9))
+//   f      = (F, F, -rd),  rd = 1 / d,  F = rd * 9
+//   p.x    = fma(Tw.z Tu.z, -rd, fma(F, Tw.x Tu.x, F * (Tw.y Tu.y)))
+//   h0.x   = fma(p.x, p.x, fma(Tu.z^2, rd, -fma(F, Tu.x^2, F * Tu.y^2)))
+#ifndef ENVGS_AABB_VARIANT
+#define ENVGS_AABB_VARIANT 0
+#endif
+__device__ __forceinline__ float dot3_ref_order(float F, float rd, float mx, float my, float mz) {
+    // F*mx + F*my + (-rd)*mz in the reference's fused order
+#if ENVGS_AABB_VARIANT == 0
+    return __fmaf_rn(mz, -rd, __fmaf_rn(F, mx, __fmul_rn(F, my)));
+#else
+    return __fmaf_rn(mz, -rd, __fmaf_rn(F, my, __fmul_rn(F, mx)));
+#endif
+}
 __device__ __forceinline__ bool compute_aabb(float3 Tu, float3 Tv, float3 Tw, float cutoff2, float2& center,
                                              float2& extent) {
-    float3 t = f3(cutoff2, cutoff2, -1.0f);
-    float d = dot(t, Tw * Tw);
+    const float wx2 = __fmul_rn(Tw.x, Tw.x), wy2 = __fmul_rn(Tw.y, Tw.y);
+#if ENVGS_AABB_VARIANT == 0
+    const float d = __fmaf_rn(-Tw.z, Tw.z, __fmaf_rn(wx2, cutoff2, __fmul_rn(wy2, cutoff2)));
+#else
+    const float d = __fmaf_rn(-Tw.z, Tw.z, __fmaf_rn(wy2, cutoff2, __fmul_rn(wx2, cutoff2)));
+#endif
     if (d == 0.0f) return false;
-    float3 f = (1.0f / d) * t;
-    float2 p = make_float2(dot(f, Tu * Tw), dot(f, Tv * Tw));
-    float2 h0 = make_float2(p.x * p.x - dot(f, Tu * Tu), p.y * p.y - dot(f, Tv * Tv));
-    center = p;
-    extent = make_float2(sqrtf(fmaxf(1e-4f, h0.x)), sqrtf(fmaxf(1e-4f, h0.y)));
+    const float rd = __fdiv_rn(1.0f, d);
+    const float F = __fmul_rn(rd, cutoff2);
+    const float px = dot3_ref_order(F, rd, __fmul_rn(Tu.x, Tw.x), __fmul_rn(Tu.y, Tw.y), __fmul_rn(Tu.z, Tw.z));
+    const float py = dot3_ref_order(F, rd, __fmul_rn(Tv.x, Tw.x), __fmul_rn(Tv.y, Tw.y), __fmul_rn(Tv.z, Tw.z));
+    const float du = dot3_ref_order(F, rd, __fmul_rn(Tu.x, Tu.x), __fmul_rn(Tu.y, Tu.y), __fmul_rn(Tu.z, Tu.z));
+    const float dv = dot3_ref_order(F, rd, __fmul_rn(Tv.x, Tv.x), __fmul_rn(Tv.y, Tv.y), __fmul_rn(Tv.z, Tv.z));
+    const float h0x = __fmaf_rn(px, px, -du), h0y = __fmaf_rn(py, py, -dv);
+    center = make_float2(px, py);
+    extent = make_float2(sqrtf(fmaxf(1e-4f, h0x)), sqrtf(fmaxf(1e-4f, h0y)));
     return true;
 }
 
@@ -346,7 +373,7 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(
                 float3 p = cross(k, l);
                 if (p.z != 0.0f) {
                     const float rz = px_rcp(p.z);                // one reciprocal instead of two divisions (<= 1 ulp apart)
-                    float sx = p.x * rz, sy = p.y * rz;
+                    float sx = px_div(p.x, p.z, rz), sy = px_div(p.y, p.z, rz);
                     float rho3d = sx * sx + sy * sy;
                     float dx = r2.y - pxf, dy = r2.z - pyf;
                     float rho2d = FILTER_INV_SQUARE * (dx * dx + dy * dy);
@@ -364,7 +391,7 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(
                                 w = alpha * T;
                                 const float4 r3 = s_r3[j];
                                 float A = 1.0f - T;
-                                float m = FAR_N / (FAR_N - NEAR_N) * (1.0f - NEAR_N * px_rcp(depth));
+                                float m = FAR_N / (FAR_N - NEAR_N) * (1.0f - px_div(NEAR_N, depth, px_rcp(depth)));
                                 distortion += (m * m * A + M2 - 2.0f * m * M1) * w;
                                 Dacc += depth * w;
                                 M1 += m * w;

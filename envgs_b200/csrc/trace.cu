@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(TR_THREADS) trace_kernel(const TraceParams p) 
                         const float3 Tm = f3(dot(tu, mu), dot(tv, mu), dot(nr, mu));
                         const float u1 = tu.x * xyz.x + tu.y * xyz.y + tu.z * xyz.z + (-Tm.x);
                         const float v1 = tv.x * xyz.x + tv.y * xyz.y + tv.z * xyz.z + (-Tm.y);
-                        const float2 uv = make_float2(u1 / scale.x, v1 / scale.y);
+                        const float2 uv = make_float2(px_div(u1, scale.x, px_rcp(scale.x)), px_div(v1, scale.y, px_rcp(scale.y)));   // same helpers as trace_fast.cu
                         const float rho3d = uv.x * uv.x + uv.y * uv.y;
                         float3 normal = nr;
                         float nsign = 1.0f;
@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(TR_THREADS) trace_kernel(const TraceParams p) 
                         const float power = -0.5f * fminf(rho3d, rho2d);
                         if (power > 0.0f) continue;
                         const float opac = a.opacities[gidx];
-                        const float G = expf(power);
+                        const float G = px_exp(power);
                         const float alpha = fminf(0.99f, opac * G);
                         if (alpha < 1.0f / 255.0f) continue;
                         T_next = T_prev * (1.0f - alpha);

@@ -486,7 +486,7 @@ __device__ __forceinline__ float eval_and_scan(const envgs_trace_args& a, bool v
         const float Tx = dot(e.tu, e.mu), Ty = dot(e.tv, e.mu);
         const float u1 = e.tu.x * e.xyz.x + e.tu.y * e.xyz.y + e.tu.z * e.xyz.z + (-Tx);
         const float v1 = e.tv.x * e.xyz.x + e.tv.y * e.xyz.y + e.tv.z * e.xyz.z + (-Ty);
-        e.uv = make_float2(u1 * px_rcp(e.scale.x), v1 * px_rcp(e.scale.y));
+        e.uv = make_float2(px_div(u1, e.scale.x, px_rcp(e.scale.x)), px_div(v1, e.scale.y, px_rcp(e.scale.y)));
         const float rho3d = e.uv.x * e.uv.x + e.uv.y * e.uv.y;
         const float cosv = -sum3((e.mu - campos) * nr);
         if (cosv == 0.0f) cand = false;

@@ -7,8 +7,16 @@ tests/test_gpu_reference.py — never by the product path.
 
 Recipe: torch.utils.cpp_extension.load on the five files of each variant with
 `-include cstdint` (gcc 13 no longer provides uint32_t/uintptr_t transitively to rasterizer_impl.h:24,40-61) and the
-vendored GLM on the include path.  The tracer needs the OptiX runtime (libnvoptix.so.1), which the GPU boxes of this pool
-do not ship (probed 2026-09-24: `OSError: libnvoptix.so.1: cannot open shared object file`), so it is not built.
+vendored GLM on the include path.
+
+Tracer: the reference host code needs the OptiX runtime (libnvoptix.so.1), which the GPU boxes of this pool do not ship
+(probe log: profiles/round2_optix_probe.txt).  Its DEVICE programs (optix_tracer/forward.cu, backward.cu) hold all of the
+surfel arithmetic and use only eight OptiX intrinsics, so they are compiled UNMODIFIED as plain CUDA against the emulation
+header oracle/optix_shim/optix.h with the small host driver oracle/ref_trace_driver.cu:
+    nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -shared -Xcompiler -fPIC \
+         -I oracle/optix_shim -I <ref>/optix_tracer -DREF_TRACE_SOURCE='"<ref>/optix_tracer/forward.cu"' -DREF_TRACE_BACKWARD=0 \
+         oracle/ref_trace_driver.cu -o oracle/_ref/ref_trace/libref_trace_fwd.so      (and backward.cu / =1 / _bwd.so)
+No fast-math flags: the reference's CMake build adds none (CMakeLists.txt, optix_tracer/CMakeLists.txt).
 """
 from __future__ import annotations
 
@@ -21,6 +29,33 @@ VARIANTS = {
     "ref_rast_wet": "diff-surfel-rasterization-wet",            # NUM_CHANNELS 3, in-kernel SH
     "ref_rast_wet_ch05": "diff-surfel-rasterization-wet-ch05",  # NUM_CHANNELS 5 (what EnvGS imports)
 }
+
+
+REF_TRACE = "/root/reference/submodules/diff-surfel-tracing/optix_tracer"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def build_tracer(verbose: bool = False) -> dict:
+    """Compile the unmodified reference tracer device programs against the OptiX emulation header (see module docstring)."""
+    import subprocess
+    if not os.path.isdir(REF_TRACE):
+        raise FileNotFoundError(f"{REF_TRACE} not present (the reference only exists in the build container)")
+    bdir = os.path.join(OUT, "ref_trace")
+    os.makedirs(bdir, exist_ok=True)
+    deps = [os.path.join(HERE, "ref_trace_driver.cu"), os.path.join(HERE, "optix_shim", "optix.h")]
+    built = {}
+    for src, flag, tag in (("forward.cu", "0", "fwd"), ("backward.cu", "1", "bwd")):
+        so = os.path.join(bdir, f"libref_trace_{tag}.so")
+        built[f"ref_trace_{tag}"] = so
+        if os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(d) for d in deps):
+            continue
+        cmd = ["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-w",
+               "-I", os.path.join(HERE, "optix_shim"), "-I", REF_TRACE,
+               f'-DREF_TRACE_SOURCE="{os.path.join(REF_TRACE, src)}"', f"-DREF_TRACE_BACKWARD={flag}", deps[0], "-o", so]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.run(cmd, check=True)
+    return built
 
 
 def build(verbose: bool = False) -> dict:
@@ -46,6 +81,7 @@ def build(verbose: bool = False) -> dict:
             extra_cuda_cflags=["-include", "cstdint", "-O3", "-gencode", "arch=compute_100a,code=sm_100a"],
             build_directory=bdir, verbose=verbose, is_python_module=False)
         built[name] = so
+    built.update(build_tracer(verbose))
     return built
 
 

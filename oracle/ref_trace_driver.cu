@@ -1,0 +1,76 @@
+// ORACLE tooling (checker only): host driver around the UNMODIFIED reference tracer device programs, compiled against
+// oracle/optix_shim/optix.h.  Built twice by oracle/build_ref.py:
+//     -DREF_TRACE_SOURCE='".../optix_tracer/forward.cu"'  -DREF_TRACE_BACKWARD=0  ->  oracle/_ref/ref_trace/libref_trace_fwd.so
+//     -DREF_TRACE_SOURCE='".../optix_tracer/backward.cu"' -DREF_TRACE_BACKWARD=1  ->  oracle/_ref/ref_trace/libref_trace_bwd.so
+// The `Params` block is filled the way the reference host code fills it
+// (/root/reference/submodules/diff-surfel-tracing/trace_surfels.cpp:233-283 forward, :382-440 backward): empty tensors
+// arrive as null pointers, `training`/`a_weights` are only set for the forward launch.
+#include REF_TRACE_SOURCE
+
+#undef __global__
+#define __global__ __attribute__((global))
+
+extern "C" __global__ void optix_shim_raygen_kernel(unsigned int num_rays)
+{
+    if (blockIdx.x * blockDim.x + threadIdx.x >= num_rays) return;
+    __raygen__ot();
+}
+
+struct RefTraceArgs
+{
+    int P, H, W, D, M;
+    int training, start_from_first, max_trace_depth;
+    float specular_threshold, scale_modifier;
+    int num_triangles;
+    const float* vertices; const int* triangles;
+    float *ray_o, *ray_d, *background, *means3D, *shs, *colors_precomp, *others_precomp, *opacities, *scales, *rotations;
+    float *viewmatrix, *projmatrix, *campos;
+    float *out_rgb, *out_dpt, *out_acc, *out_dist, *out_norm, *out_aux, *mid_val, *a_weights;
+    float *dL_drgb, *dL_ddpt, *dL_dacc, *dL_ddist, *dL_dnorm, *dL_daux;
+    float *dL_dray_o, *dL_dray_d, *dL_dmeans3D, *dL_dshs, *dL_dcolors, *dL_dothers, *dL_dopacities, *dL_dscales, *dL_drotations,
+          *dL_dtransMat;
+};
+
+extern "C" int ref_trace_launch(const RefTraceArgs* a, void* stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    OptixShimScene scene{a->vertices, a->triangles, (unsigned)a->num_triangles};
+    OptixShimScene* d_scene = nullptr;
+    if (cudaMalloc(&d_scene, sizeof(scene)) != cudaSuccess) return -1;
+    cudaMemcpyAsync(d_scene, &scene, sizeof(scene), cudaMemcpyHostToDevice, stream);
+
+    Params p;
+    memset(&p, 0, sizeof(p));
+    p.handle = reinterpret_cast<OptixTraversableHandle>(d_scene);
+    p.training = a->training != 0;
+    p.max_trace_depth = a->max_trace_depth;
+    p.start_from_first = a->start_from_first != 0;
+    p.specular_threshold = a->specular_threshold;
+    p.P = a->P; p.H = a->H; p.W = a->W; p.D = a->D; p.M = a->M;
+    p.ray_o = (float3*)a->ray_o; p.ray_d = (float3*)a->ray_d; p.vertices = (float3*)a->vertices;
+    p.background = a->background; p.means3D = (float3*)a->means3D; p.shs = (float3*)a->shs;
+    p.colors_precomp = a->colors_precomp; p.others_precomp = a->others_precomp; p.opacities = a->opacities;
+    p.scales = (float2*)a->scales; p.scale_modifier = a->scale_modifier; p.rotations = (float4*)a->rotations;
+    p.transMat_precomp = nullptr; p.viewmatrix = a->viewmatrix; p.projmatrix = a->projmatrix; p.campos = (float3*)a->campos;
+    p.out_rgb = a->out_rgb; p.out_dpt = a->out_dpt; p.out_acc = a->out_acc; p.out_dist = (float3*)a->out_dist;
+    p.out_norm = (float3*)a->out_norm; p.out_aux = a->out_aux; p.mid_val = a->mid_val; p.a_weights = a->a_weights;
+    p.dL_drgb = a->dL_drgb; p.dL_ddpt = a->dL_ddpt; p.dL_dacc = a->dL_dacc; p.dL_ddist = a->dL_ddist;
+    p.dL_dnorm = (float3*)a->dL_dnorm; p.dL_daux = a->dL_daux;
+    p.dL_dray_o = (float3*)a->dL_dray_o; p.dL_dray_d = (float3*)a->dL_dray_d; p.dL_dmeans3D = (float3*)a->dL_dmeans3D;
+    p.dL_dshs = (float3*)a->dL_dshs; p.dL_dcolors = a->dL_dcolors; p.dL_dothers = a->dL_dothers;
+    p.dL_dopacities = a->dL_dopacities; p.dL_dscales = (float2*)a->dL_dscales; p.dL_drotations = (float4*)a->dL_drotations;
+    p.dL_dtransMat_precomp = a->dL_dtransMat;
+
+    uint3 dim = make_uint3((unsigned)a->H, (unsigned)a->W, 1u);
+    cudaMemcpyToSymbolAsync(params, &p, sizeof(Params), 0, cudaMemcpyHostToDevice, stream);
+    cudaMemcpyToSymbolAsync(optix_shim_dim, &dim, sizeof(dim), 0, cudaMemcpyHostToDevice, stream);
+    const unsigned int n = (unsigned)a->H * (unsigned)a->W;
+    optix_shim_raygen_kernel<<<(n + OPTIX_SHIM_BLOCK - 1) / OPTIX_SHIM_BLOCK, OPTIX_SHIM_BLOCK, 0, stream>>>(n);
+    cudaError_t e = cudaStreamSynchronize(stream);
+    cudaFree(d_scene);
+    if (e != cudaSuccess) return -(int)e - 100;
+    e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : -(int)e - 100;
+}
+
+extern "C" int ref_trace_is_backward() { return REF_TRACE_BACKWARD; }

@@ -22,10 +22,12 @@ Backward comes from autograd, with the reference's deviations reproduced (backwa
 Third-party arithmetic outside /root/reference: the ray/triangle distance `t` comes from NVIDIA OptiX 7.7 (closed
 source, driver-side libnvoptix; headers vendored at third_party/optix @ 7b5c4e86).  Its specification here is the
 analytic ray-plane distance the reference's own backward differentiates (backward.cu:293-302).
-Pinning status: PARITY UNPINNED for the tracer unless tests/golden/trace_ref_*.pt exist (they need an OptiX-capable
-driver on the GPU box, see oracle/make_golden.py and DESIGN.md §oracle).
-Ignored reference quirk: hits within 1e-5 (in t) behind every 16th hit are skipped by the chunk restart
-(forward.cu:438-441); the brute-force list keeps them.
+Pinning status: PINNED by tests/golden/trace_ref_*.pt — outputs of the UNMODIFIED reference device programs
+(optix_tracer/forward.cu, backward.cu) compiled against the OptiX emulation header oracle/optix_shim/optix.h (recipe:
+oracle/build_ref.py, generator: oracle/make_golden.py, checked by tests/test_oracle_golden.py).  What remains outside the
+pin is only OptiX's own ray/triangle distance, emulated there by fp64 Moeller-Trumbore.
+Chunk restart (forward.cu:288-441): the reference fetches hits 16 at a time and restarts the ray at
+t_last + STEP_EPSILON, so a hit within 1e-5 (in t) behind every 16th hit is never seen; `_chunk_restart_keep` restates it.
 """
 from __future__ import annotations
 
@@ -51,6 +53,35 @@ class TraceOut:
     aux: torch.Tensor    # (H,W,2)
     mid: torch.Tensor    # (H,W,32)
     wet: torch.Tensor    # (P,1)
+    border: torch.Tensor = None   # (H,W) bool: a discrete decision on this ray lies within fp32 noise of its threshold
+
+
+# Relative width of the "either side is right" band around the discrete per-hit decisions (alpha >= 1/255, |u|,|v| <= 3,
+# cmd >= min depth, rho3d <= rho2d).  fp32 evaluation of a hit at distance t ~ 20 carries ~5 ulp of position error, i.e.
+# ~7e-5 relative in alpha (tools/trace_diag.py, profiles/round2_parity_experiments.md): the reference's own fp32 result
+# and any other fp32 evaluation (including real OptiX's hit distance vs the emulation's) may land on different sides.
+BORDER_REL = 3e-4
+
+
+def _chunk_restart_keep(tk: torch.Tensor, hk: torch.Tensor) -> torch.Tensor:
+    """Which entries of the per-ray sorted hit list (r,k) the reference's chunked traversal ever sees (forward.cu:288-441):
+    after a full chunk of CHUNK_SIZE = 16 hits the next optixTrace starts at ray_o + (t_16th + STEP_EPSILON) * ray_d with
+    tmin = 0, so hits with t <= t_16th + 1e-5 beyond the 16th are dropped."""
+    r, k = tk.shape
+    keep = hk.clone()
+    nh = hk.sum(1)
+    start = torch.zeros(r, dtype=torch.long, device=tk.device)
+    idx = torch.arange(k, device=tk.device)[None]
+    for _ in range((k + 15) // 16):
+        e = start + 15
+        valid = e < nh
+        if not bool(valid.any()):
+            break
+        t_end = tk.gather(1, e.clamp(max=k - 1)[:, None])[:, 0]
+        drop = valid[:, None] & (idx > e[:, None]) & hk & (tk <= (t_end + STEP_EPSILON)[:, None])
+        keep &= ~drop
+        start = torch.where(valid, e + 1 + drop.sum(1), torch.full_like(start, k))
+    return keep
 
 
 def _segment(ray_o, ray_d, pix, active, means, scales, rotations, opacities, shs, sh_degree, colors, others, campos, bg,
@@ -84,12 +115,15 @@ def _segment(ray_o, ray_d, pix, active, means, scales, rotations, opacities, shs
             u = ((x * tu[None]).sum(-1) - (means * tu).sum(-1)[None]) / scales[None, :, 0]
             v = ((x * tv[None]).sum(-1) - (means * tv).sum(-1)[None]) / scales[None, :, 1]
             hit = (q != 0) & (t > 0) & (t < 1e16) & (u.abs() <= 3) & (v.abs() <= 3) & act[:, None] & torch.isfinite(t)
+            emax = torch.maximum(u.abs(), v.abs())
+            near_edge = ((q != 0) & (t > 0) & act[:, None] & torch.isfinite(t) & ((emax - 3.0).abs() <= 3.0 * BORDER_REL)).any(1)
             tkey = torch.where(hit, t, torch.full_like(t, float("inf")))
             k = min(max_hits, P)
             tk, ik = torch.topk(tkey, k, dim=1, largest=False, sorted=True)       # (r,k)
             hk = torch.isfinite(tk)
             if k < P and bool((hit.sum(1) > k).any()):
                 raise RuntimeError("trace oracle: max_hits too small for this scene")
+            hk = _chunk_restart_keep(tk, hk)
         # differentiable re-evaluation of the selected hits
         mu, sc, mv = means[ik], scales[ik], mvec[ik]                  # (r,k,3) ...
         qd = (mv * d[:, None]).sum(-1)
@@ -129,6 +163,11 @@ def _segment(ray_o, ray_d, pix, active, means, scales, rotations, opacities, shs
         oG = opacities[ik, 0] * torch.exp(power)
         alpha = oG + (torch.clamp(oG, max=0.99) - oG).detach()
         cand = hk & cos_ok & (~skip_xy) & (cmd >= min_depth) & (power <= 0) & (alpha >= 1.0 / 255.0)
+        with torch.no_grad():
+            thr = 1.0 / 255.0
+            nb_ = hk & cos_ok & (((alpha - thr).abs() <= BORDER_REL * thr) | ((cmd - min_depth).abs() <= BORDER_REL * min_depth))
+            if first:
+                nb_ = nb_ | (hk & ((rho3d - rho2d).abs() <= BORDER_REL * rho2d.abs()))
         one_m = torch.where(cand, 1.0 - alpha, torch.ones_like(alpha))
         Tincl = torch.cumprod(one_m, dim=1)
         Tbefore = torch.cat([torch.ones(r, 1, dtype=dt, device=dev), Tincl[:, :-1]], dim=1)
@@ -136,6 +175,9 @@ def _segment(ray_o, ray_d, pix, active, means, scales, rotations, opacities, shs
         alive = torch.cumsum(stop.to(torch.int32), dim=1) == 0
         nth = torch.cumsum((cand & alive).to(torch.int32), dim=1)          # 1-based contributor count
         contrib = cand & alive & (nth <= MAX_INTERSECTION)
+        with torch.no_grad():   # hits behind the termination point cannot change the result
+            alive_before = torch.cat([torch.ones(r, 1, dtype=torch.bool, device=dev), alive[:, :-1]], dim=1)
+            border = near_edge | (nb_ & alive_before).any(1) | (cand & ((Tincl - 0.0001).abs() <= 1e-2 * 0.0001) & alive_before).any(1)
         w = torch.where(contrib, alpha * Tbefore, torch.zeros_like(alpha))
         Tfinal = torch.where(contrib, one_m, torch.ones_like(one_m)).prod(dim=1)
 
@@ -160,9 +202,9 @@ def _segment(ray_o, ray_d, pix, active, means, scales, rotations, opacities, shs
         Nn = (w[..., None] * normal).sum(1)
         A = 1.0 - Tfinal
         wet = wet.index_add(0, ik.reshape(-1), w.detach().reshape(-1))
-        outs.append((Cc, D, A, Nn, dist, mw.sum(1), mmw.sum(1), O))
+        outs.append((Cc, D, A, Nn, dist, mw.sum(1), mmw.sum(1), O, border))
     cat = lambda i: torch.cat([o[i] for o in outs], dim=0)
-    return cat(0), cat(1), cat(2), cat(3), cat(4), cat(5), cat(6), cat(7), wet
+    return cat(0), cat(1), cat(2), cat(3), cat(4), cat(5), cat(6), cat(7), wet, cat(8)
 
 
 def trace(ray_o, ray_d, means3D, opacities, scales, rotations, shs=None, colors_precomp=None, others_precomp=None, *,
@@ -188,10 +230,11 @@ def trace(ray_o, ray_d, means3D, opacities, scales, rotations, shs=None, colors_
     mids = []
     for i in range(max_trace_depth + 1):
         first = (i == 0) and start_from_first
-        Cc, D, A, Nn, dist, M1, M2, O, wet = _segment(o, d, pix, active, means3D, scales, rotations, opacities, shs, sh_degree,
+        Cc, D, A, Nn, dist, M1, M2, O, wet, brd = _segment(o, d, pix, active, means3D, scales, rotations, opacities, shs, sh_degree,
                                                       colors_precomp, others_precomp, campos, bgv, first, projmatrix, W, H,
                                                       scale_modifier, max_hits, ray_chunk)
         wet_total = wet_total + wet
+        border_total = brd if i == 0 else (border_total | (brd & active))
         a = active.to(dt)
         if i == 0:
             out_dpt, out_norm, out_aux = D, Nn, O
@@ -218,4 +261,5 @@ def trace(ray_o, ray_d, means3D, opacities, scales, rotations, shs=None, colors_
         mids.append(torch.zeros(R_, 16, dtype=dt, device=dev))
     mid = torch.cat(mids, dim=-1).detach()
     return TraceOut(rgb.reshape(H, W, 3), out_dpt.reshape(H, W, 1), out_acc.reshape(H, W, 1), out_norm.reshape(H, W, 3),
-                    out_dist.reshape(H, W, 1), out_aux.reshape(H, W, 2), mid.reshape(H, W, 32), wet_total[:, None])
+                    out_dist.reshape(H, W, 1), out_aux.reshape(H, W, 2), mid.reshape(H, W, 32), wet_total[:, None],
+                    border_total.reshape(H, W))

@@ -195,9 +195,12 @@ def run_cuda_trace(env, cam, ray_o, ray_d, *, use_sh=True, others=False, start_f
 
 
 def run_oracle_trace(env, cam, ray_o, ray_d, *, use_sh=True, others=False, start_from_first=False, max_trace_depth=0,
-                     specular_threshold=0.0, grads=None, dtype=torch.float64, bg=None, max_hits=96, ray_chunk=2048):
-    bg = torch.zeros(3) if bg is None else bg
-    leaf = lambda t: t.to(dtype).clone().requires_grad_(True)
+                     specular_threshold=0.0, grads=None, dtype=torch.float64, bg=None, max_hits=96, ray_chunk=2048, device="cpu"):
+    """`device="cuda"` only moves the checker's own torch arithmetic (fp64) to the GPU for the large live tests."""
+    dev = torch.device(device)
+    bg = (torch.zeros(3) if bg is None else bg).to(dev)
+    cam = cam.to(dev)
+    leaf = lambda t: t.to(device=dev, dtype=dtype).clone().requires_grad_(True)
     means, opac, scales, rots = leaf(env.means), leaf(env.opacities), leaf(env.scales), leaf(env.rotations)
     ro, rd = leaf(ray_o), leaf(ray_d)
     shs = colors = oth = None
@@ -210,20 +213,61 @@ def run_oracle_trace(env, cam, ray_o, ray_d, *, use_sh=True, others=False, start
     res = TO.trace(ro, rd, means, opac, scales, rots, shs=shs, colors_precomp=colors, others_precomp=oth, sh_degree=3,
                    campos=cam.campos, bg=bg, start_from_first=start_from_first, max_trace_depth=max_trace_depth,
                    specular_threshold=specular_threshold, projmatrix=cam.projmatrix, max_hits=max_hits, ray_chunk=ray_chunk)
-    out = dict(rgb=res.rgb.detach().float(), dpt=res.dpt.detach().float(), acc=res.acc.detach().float(),
-               norm=res.norm.detach().float(), dist=res.dist.detach().float(), aux=res.aux.detach().float(),
-               mid=res.mid.float(), wet=res.wet.detach().float())
+    c = lambda t: t.detach().float().cpu()
+    out = dict(rgb=c(res.rgb), dpt=c(res.dpt), acc=c(res.acc), norm=c(res.norm), dist=c(res.dist), aux=c(res.aux),
+               mid=c(res.mid), wet=c(res.wet), border=res.border.cpu())
     if grads is not None:
-        loss = sum((t * grads[k].to(dtype)).sum() for k, t in dict(rgb=res.rgb, dpt=res.dpt, acc=res.acc, norm=res.norm, aux=res.aux).items())
+        loss = sum((t * grads[k].to(device=dev, dtype=dtype)).sum()
+                   for k, t in dict(rgb=res.rgb, dpt=res.dpt, acc=res.acc, norm=res.norm, aux=res.aux).items())
         loss.backward()
-        z = lambda t, ref: torch.zeros_like(ref).float() if t.grad is None else t.grad.float()
+        z = lambda t, ref: torch.zeros_like(ref).float().cpu() if t.grad is None else t.grad.float().cpu()
         out.update(g_means=z(means, means), g_opac=z(opac, opac), g_scales=z(scales, scales), g_rots=z(rots, rots),
                    g_ray_o=z(ro, ro), g_ray_d=z(rd, rd))
-        out["g_grads3D"] = out["g_means"] * (env.means - cam.campos[None]).norm(dim=-1, keepdim=True) / 2
+        out["g_grads3D"] = out["g_means"] * (env.means - cam.campos.cpu()[None]).norm(dim=-1, keepdim=True) / 2
         if use_sh:
             out.update(g_shs=z(shs, shs))
         else:
             out.update(g_colors=z(colors, colors))
         if others:
             out.update(g_others=z(oth, oth))
+    return out
+
+
+def run_reference_trace(env, cam, ray_o, ray_d, *, use_sh=True, others=False, start_from_first=False, max_trace_depth=0,
+                        specular_threshold=0.0, grads=None, device="cuda", training=True, bg=None):
+    """The UNMODIFIED reference tracer programs (oracle/_ref/ref_trace, OptiX traversal emulated by brute force) on the
+    same inputs as run_cuda_trace, wrapped the way diff_surfel_tracing/__init__.py:51-204 wraps them."""
+    from oracle import ref_trace as RT
+    dev = torch.device(device)
+    bg = torch.zeros(3) if bg is None else bg
+    means, opac, scales, rots = (t.to(dev) for t in (env.means, env.opacities, env.scales, env.rotations))
+    shs = colors = oth = None
+    if use_sh:
+        shs = env.shs.to(dev)
+    else:
+        colors = torch.clamp_min(env.shs[:, 0, :] * 0.28209479177387814 + 0.5, 0.0).to(dev)
+    if others:
+        oth = torch.cat([env.specular, env.roughness], -1).to(dev)
+    v, f = scene.quad_vertices(means, scales, rots)
+    kw = dict(ray_o=ray_o.to(dev), ray_d=ray_d.to(dev), vertices=v, triangles=f, bg=bg.to(dev), means3D=means, shs=shs, degree=3,
+              colors_precomp=colors, others_precomp=oth, opacities=opac, scales=scales, scale_modifier=1.0, rotations=rots,
+              viewmatrix=cam.viewmatrix.to(dev), projmatrix=cam.projmatrix.to(dev), campos=cam.campos.to(dev),
+              start_from_first=start_from_first, max_trace_depth=max_trace_depth, specular_threshold=specular_threshold)
+    fwd = RT.trace_forward(training=training, **kw)
+    out = {k: fwd[k].cpu() for k in ("rgb", "dpt", "acc", "norm", "aux", "mid", "wet")}
+    out["dist"] = fwd["dist"][..., :1].cpu()
+    if grads is not None:
+        H, W = ray_o.shape[:2]
+        up = dict(grads)
+        up.setdefault("dist", torch.zeros(H, W, 1))
+        bw = RT.trace_backward(fwd, up, **kw)
+        out.update(g_means=bw["g_means"].cpu(), g_opac=bw["g_opac"].cpu(), g_scales=bw["g_scales"].cpu(), g_rots=bw["g_rots"].cpu(),
+                   g_ray_o=bw["g_ray_o"].cpu(), g_ray_d=bw["g_ray_d"].cpu())
+        out["g_grads3D"] = out["g_means"] * (env.means - cam.campos[None]).norm(dim=-1, keepdim=True) / 2
+        if use_sh:
+            out["g_shs"] = bw["g_shs"].cpu()
+        else:
+            out["g_colors"] = bw["g_colors"].cpu()
+        if others:
+            out["g_others"] = bw["g_others"].cpu()
     return out

@@ -18,14 +18,24 @@ def test_cuda_matches_reference_golden(built_lib, name):
     base, cam, feats, gc, go, bg, use_sh, C = MG.case_inputs(name)
     assert abs(MG.input_checksum(base, cam, feats, gc, go) - gold["input_checksum"]) <= 1e-6 * gold["input_checksum"]
     cu = Hh.run_cuda_raster(base, cam, C, feats=feats, use_sh=use_sh, g_color=gc, g_others=go, bg=bg)
+    # BASELINE.json's tolerances, unmodified: 1e-4 on every rendered value (allmap scaled by its magnitude: depths), 1e-3 on the
+    # FULL relative L2 norm of every gradient; the integer outputs bit-exact.
+    assert torch.equal(cu["radii"], gold["radii"])
     for key in ("color", "allmap"):
         scale = max(1.0, float(gold[key].abs().max())) if key == "allmap" else 1.0
-        assert Hh.frac_above(cu[key], gold[key], 1e-4 * scale) <= 1e-3, Hh.image_report(key, cu[key], gold[key])
-        assert float((cu[key] - gold[key]).abs().max()) <= 3e-2 * scale, Hh.image_report(key, cu[key], gold[key])
-    assert int((cu["radii"] != gold["radii"]).sum()) <= max(1, gold["radii"].numel() // 1000)
-    assert Hh.rel_l2(cu["weight"], gold["weight"]) < 1e-3
+        assert float((cu[key] - gold[key]).abs().max()) <= 1e-4 * scale, Hh.image_report(key, cu[key], gold[key])
+    assert Hh.rel_l2(cu["weight"], gold["weight"]) < 1e-4
     for k in [k for k in gold if k.startswith("g_")]:
-        t, full = Hh.trimmed_rel_l2(cu[k], gold[k]), Hh.rel_l2(cu[k], gold[k])
-        tol = 2e-2 if k == "g_means2D" else 1e-3   # see tests/test_oracle_golden.py
-        assert t <= tol, f"{k}: trimmed rel L2 {t:.3e} (full {full:.3e})"
-        assert full <= 5e-2, f"{k}: rel L2 {full:.3e}"
+        assert Hh.rel_l2(cu[k], gold[k]) <= 1e-3, f"{k}: rel L2 {Hh.rel_l2(cu[k], gold[k]):.3e}"
+
+
+@pytest.mark.parametrize("name", list(MG.TRACE_CASES))
+def test_cuda_trace_matches_reference_golden(built_lib, name):
+    """The LBVH tracer (through SurfelTracer, i.e. the C ABI) against the UNMODIFIED reference device programs' outputs
+    (tests/golden/trace_ref_*.pt): BASELINE.json's 1e-4 on rendered values, 1e-3 full relative L2 on gradients."""
+    from tests.test_oracle_golden import check_trace_against_golden, oracle_for_trace_case
+    gold = torch.load(os.path.join(GOLD, name + ".pt"))
+    env, cam, ro, rd, up, kw = MG.trace_case_inputs(name)
+    assert abs(MG.trace_input_checksum(env, cam, ro, rd) - gold["input_checksum"]) <= 1e-6 * gold["input_checksum"]
+    cu = Hh.run_cuda_trace(env, cam, ro, rd, grads=up, **kw)
+    check_trace_against_golden(cu, gold, kw, oracle_for_trace_case(name, grads=False)["border"])

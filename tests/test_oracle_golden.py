@@ -39,3 +39,71 @@ def test_reference_atomics_noise_is_below_tolerance():
     for name in MG.CASES:
         gold = torch.load(os.path.join(GOLD, name + ".pt"))
         assert gold["noise_g_means"] < 1e-5
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Tracer: the oracle against golden vectors produced by the UNMODIFIED reference device programs (optix_tracer/forward.cu,
+# backward.cu compiled against oracle/optix_shim/optix.h; oracle/make_golden.py).  Tolerances are BASELINE.json's:
+# 1e-4 on every rendered value (scaled by the output's magnitude where it exceeds 1: depths reach ~20), 1e-3 on the full
+# relative L2 norm of every gradient.
+TRACE_IMG_TOL = 1e-4
+TRACE_GRAD_TOL = 1e-3
+
+
+def trace_mid_mask(gold, kw):
+    """`mid_val` slots of a segment the path never reached hold uninitialised local memory in the reference (forward.cu:571
+    declares `float mid_val[...]` without initialiser and :605-610 copies all of it out), so only segments that ran compare."""
+    ran0 = torch.ones_like(gold["mid"][..., 0], dtype=torch.bool)
+    if kw.get("max_trace_depth", 0) == 0:
+        return ran0, torch.zeros_like(ran0)
+    ran1 = (gold["mid"][..., 8:11].norm(dim=-1) != 0) & (gold["mid"][..., 11] > kw["specular_threshold"])
+    return ran0, ran1
+
+
+BORDER_TOL = 2e-2     # a flipped borderline hit moves a ray by at most its own weight (alpha*T <= 0.011 at the quad edge)
+
+
+def check_trace_against_golden(out, gold, kw, border, img_tol=TRACE_IMG_TOL, grad_tol=TRACE_GRAD_TOL):
+    """`border` (H,W) bool from the fp64 oracle: rays on which a discrete per-hit decision (alpha >= 1/255, quad edge, min
+    depth) lies within fp32 noise of its threshold (oracle/trace_oracle.py BORDER_REL) — there either outcome is a correct
+    fp32 evaluation, so those rays get the one-flipped-hit bound instead of 1e-4.  Everything else is strict."""
+    assert float(border.float().mean()) <= 0.3
+    strict = ~border
+    for k in ("rgb", "dpt", "acc", "norm", "aux", "dist"):
+        scale = max(1.0, float(gold[k].abs().max()))
+        d = (out[k] - gold[k]).abs().amax(-1)
+        assert float(d[strict].max()) <= img_tol * scale, Hh.image_report(k, out[k], gold[k], img_tol * scale)
+        if k != "dpt" and kw.get("max_trace_depth", 0) == 0:
+            assert float(d.max()) <= BORDER_TOL * scale, Hh.image_report(k, out[k], gold[k], img_tol * scale)
+    _, ran1 = trace_mid_mask(gold, kw)
+    a, b = out["mid"].clone(), gold["mid"].clone()
+    a[..., 16:][~ran1] = 0
+    b[..., 16:][~ran1] = 0
+    scale = max(1.0, float(b.abs().max()))
+    assert float((a - b).abs().amax(-1)[strict].max()) <= img_tol * scale * 10, Hh.image_report("mid", a, b)   # segment-2 origins: 1e-3
+    assert Hh.rel_l2(out["wet"].reshape(-1), gold["wet"].reshape(-1)) <= 1e-4
+    for k in [k for k in gold if k.startswith("g_")]:
+        assert Hh.rel_l2(out[k], gold[k]) <= grad_tol, f"{k}: rel L2 {Hh.rel_l2(out[k], gold[k]):.3e}"
+
+
+def oracle_for_trace_case(name, grads=True):
+    env, cam, ro, rd, up, kw = MG.trace_case_inputs(name)
+    okw = dict(kw)
+    if "dense" in name:
+        okw.update(max_hits=1024, ray_chunk=256)
+    return Hh.run_oracle_trace(env, cam, ro, rd, grads=up if grads else None, **okw)
+
+
+@pytest.mark.parametrize("name", list(MG.TRACE_CASES))
+def test_trace_oracle_matches_reference_golden(name):
+    gold = torch.load(os.path.join(GOLD, name + ".pt"))
+    env, cam, ro, rd, up, kw = MG.trace_case_inputs(name)
+    assert abs(MG.trace_input_checksum(env, cam, ro, rd) - gold["input_checksum"]) <= 1e-6 * gold["input_checksum"]
+    orc = oracle_for_trace_case(name)
+    check_trace_against_golden(orc, gold, kw, orc["border"])
+
+
+def test_trace_reference_atomics_noise_is_below_tolerance():
+    for name in MG.TRACE_CASES:
+        gold = torch.load(os.path.join(GOLD, name + ".pt"))
+        assert gold.get("noise_g_means") is None or gold["noise_g_means"] < 1e-5
