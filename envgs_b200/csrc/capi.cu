@@ -172,7 +172,7 @@ int envgs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
 
 size_t envgs_raster_geom_bytes(int32_t P) { return GeomState::carve(nullptr, P, nullptr, scan_temp_bytes(P)); }
 size_t envgs_raster_img_bytes(int32_t width, int32_t height) { return ImageState::carve(nullptr, width, height, nullptr); }
-size_t envgs_raster_binning_bytes(int32_t n) { return BinningState::carve(nullptr, n, nullptr, sort_temp_bytes(n)); }
+size_t envgs_raster_binning_bytes(int32_t n) { return BinningState::carve(nullptr, n, nullptr, sort_temp_bytes(n), 7); }   // upper bound over C = 3, 5, 7
 
 envgs_tracer* envgs_tracer_create(void) {
     envgs_tracer* h = new (std::nothrow) envgs_tracer();

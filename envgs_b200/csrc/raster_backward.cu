@@ -9,6 +9,7 @@
 //                          (backward.cu:443-630), including the densification-signal overwrite (:626-629).
 #include "raster_state.cuh"
 #include "glm_order.cuh"
+#include "tma.cuh"
 
 namespace envgs {
 
@@ -22,18 +23,34 @@ constexpr int NG_FIX = 15;       // reduced values besides colour: normal(3) opa
 #define RBWD_MINBLOCKS 2
 #endif
 template <int C>
+__device__ __forceinline__ void issue_stage_bwd(TileStage<C>* st, uint64_t* bar, const BinningState& b, int first, int nb) {
+    // same copy set as the forward kernel's issue_stage (raster_forward.cu); entries [first, first + nb) of the tile list
+    const int a0 = first & ~3;
+    const uint32_t cnt = (uint32_t)(((first & 3) + nb + 3) & ~3);
+    mbar_arrive_expect_tx(bar, cnt * (uint32_t)(64 + 8 + 4 + 4 * C));
+    bulk_g2s(st->r0, b.srec[0] + a0, cnt * 16u, bar);
+    bulk_g2s(st->r1, b.srec[1] + a0, cnt * 16u, bar);
+    bulk_g2s(st->r2, b.srec[2] + a0, cnt * 16u, bar);
+    bulk_g2s(st->r3, b.srec[3] + a0, cnt * 16u, bar);
+    bulk_g2s(st->box, b.sbox + a0, cnt * 8u, bar);
+    bulk_g2s(st->id, b.sid + a0, cnt * 4u, bar);
+#pragma unroll
+    for (int ch = 0; ch < C; ch++) bulk_g2s(st->feat[ch], b.sfeat + (size_t)ch * b.cap + a0, cnt * 4u, bar);
+}
+
+template <int C>
 __global__ void __launch_bounds__(256, RBWD_MINBLOCKS) render_bwd_kernel(
-    const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int tiles_x,
-    const float* __restrict__ bg, const float4* __restrict__ rec, const short4* __restrict__ pixbox,
-    const float* __restrict__ features, const float* __restrict__ final_Ts, const uint32_t* __restrict__ n_contrib,
+    const uint2* __restrict__ ranges, const BinningState b, int W, int H, int tiles_x, const float* __restrict__ bg,
+    const float* __restrict__ final_Ts, const uint32_t* __restrict__ n_contrib,
     const float* __restrict__ dL_dpixels, const float* __restrict__ dL_dothers, float* __restrict__ dL_dtransMat,
     float* __restrict__ dL_dmean2D, float* __restrict__ dL_dnormal3D, float* __restrict__ dL_dopacity,
     float* __restrict__ dL_dcolors) {
+    static_assert(BB == 256, "the bulk-copy staging assumes 256-entry batches (TileStage)");
     constexpr int NG = C + NG_FIX;   // per-surfel reduced values: [0,C) colour, C..C+2 normal, C+3 opacity, C+4..C+12 dT, C+13,C+14 dmean2D
-    __shared__ float4 s_r0[BB], s_r1[BB], s_r2[BB], s_r3[BB];
-    __shared__ short4 s_box[BB];
-    __shared__ int s_id[BB];
-    __shared__ float s_feat[BB * C];
+    // two staging buffers filled by bulk asynchronous copies (tma.cuh): batch i+1 is in flight while batch i is processed
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TileStage<C>* stages = reinterpret_cast<TileStage<C>*>(smem_raw);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + 2 * sizeof(TileStage<C>));
     __shared__ uint32_t s_max;
 
     const int tile = blockIdx.x;
@@ -53,7 +70,12 @@ __global__ void __launch_bounds__(256, RBWD_MINBLOCKS) render_bwd_kernel(
     const uint32_t last_contributor = inside ? n_contrib[pix_id] : 0u;
     const uint32_t median_contributor = inside ? n_contrib[pix_id + HW] : 0u;
 
-    if (tid == 0) s_max = 0;
+    if (tid == 0) {
+        s_max = 0;
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_init_fence();
+    }
     __syncthreads();
     {
         uint32_t m = __reduce_max_sync(0xffffffffu, last_contributor);
@@ -102,22 +124,19 @@ __global__ void __launch_bounds__(256, RBWD_MINBLOCKS) render_bwd_kernel(
     const float final_A = 1.0f - T_final;
 
     const int rounds = (total + BB - 1) / BB;
+    // batch i covers the 1-based list positions pos = total - i*BB - t, t = 0..nb-1 (descending), i.e. the ascending index
+    // range [range.x + total - i*BB - nb, range.x + total - i*BB) of the sorted arrays; entry t sits at lead + nb - 1 - t
+    if (tid == 0) { const int nb0 = min(BB, total); issue_stage_bwd<C>(&stages[0], &bars[0], b, (int)range.x + total - nb0, nb0); }
     for (int i = 0; i < rounds; i++) {
-        // positions are 1-based; this batch covers pos = total - i*BB - t, t = 0..nb-1 (descending)
         const int nb = min(BB, total - i * BB);
-        if (tid < nb) {
-            int pos = total - i * BB - tid;
-            int id = (int)point_list[range.x + pos - 1];
-            s_id[tid] = id;
-            s_r0[tid] = rec[4 * (size_t)id + 0];
-            s_r1[tid] = rec[4 * (size_t)id + 1];
-            s_r2[tid] = rec[4 * (size_t)id + 2];
-            s_r3[tid] = rec[4 * (size_t)id + 3];
-            s_box[tid] = pixbox[id];
-#pragma unroll
-            for (int ch = 0; ch < C; ch++) s_feat[ch * BB + tid] = features[(size_t)id * C + ch];
+        __syncthreads();   // everyone is past batch i-1: its buffer (the one batch i+1 goes into) may be overwritten
+        if (tid == 0 && i + 1 < rounds) {
+            const int nbn = min(BB, total - (i + 1) * BB);
+            issue_stage_bwd<C>(&stages[(i + 1) & 1], &bars[(i + 1) & 1], b, (int)range.x + total - (i + 1) * BB - nbn, nbn);
         }
-        __syncthreads();
+        mbar_wait(&bars[i & 1], (i >> 1) & 1);
+        const TileStage<C>& st = stages[i & 1];
+        const int top = (((int)range.x + total - i * BB - nb) & 3) + nb - 1;   // staged slot of entry t is top - t
 
         // Candidate compaction: 32 staged surfels are box-tested at once (one per lane) against this warp's 8x4 pixel
         // block and the ballot is walked bit by bit, so a rejected surfel costs no loop iteration at all (63 % of the
@@ -127,7 +146,7 @@ __global__ void __launch_bounds__(256, RBWD_MINBLOCKS) render_bwd_kernel(
         {
             const int jj = c0 + lane;
             if (jj < nb && (uint32_t)(total - i * BB - jj) <= warp_last) {
-                const short4 bb = s_box[jj];
+                const short4 bb = st.box[top - jj];
                 cand = !(bb.x > wx1 || bb.z < wx0 || bb.y > wy1 || bb.w < wy0);
             }
         }
@@ -136,7 +155,8 @@ __global__ void __launch_bounds__(256, RBWD_MINBLOCKS) render_bwd_kernel(
             const int j = c0 + __ffs(cmask) - 1;
             cmask &= cmask - 1;
             const uint32_t pos = (uint32_t)(total - i * BB - j);
-            const float4 r0 = s_r0[j], r1 = s_r1[j], r2 = s_r2[j];
+            const int sj = top - j;
+            const float4 r0 = st.r0[sj], r1 = st.r1[sj], r2 = st.r2[sj];
             const float3 Tu = f3(r0.x, r0.y, r0.z), Tv = f3(r0.w, r1.x, r1.y), Tw = f3(r1.z, r1.w, r2.x);
 
             float g[32];
@@ -163,14 +183,14 @@ __global__ void __launch_bounds__(256, RBWD_MINBLOCKS) render_bwd_kernel(
                         const float alpha = fminf(ALPHA_MAX, opa * G);
                         if (alpha >= ALPHA_MIN) {
                             contrib = true;
-                            const float4 r3 = s_r3[j];
+                            const float4 r3 = st.r3[sj];
                             const float r1ma = px_rcp(1.0f - alpha);
                             T = T * r1ma;
                             const float w = alpha * T;
                             float dL_dalpha = 0.0f;
 #pragma unroll
                             for (int ch = 0; ch < C; ch++) {
-                                const float c = s_feat[ch * BB + j];
+                                const float c = st.feat[ch][sj];
                                 accum_rec[ch] = last_alpha * last_color[ch] + (1.0f - last_alpha) * accum_rec[ch];
                                 last_color[ch] = c;
                                 dL_dalpha += (c - accum_rec[ch]) * dL_dpixel[ch];
@@ -234,10 +254,9 @@ __global__ void __launch_bounds__(256, RBWD_MINBLOCKS) render_bwd_kernel(
             if (cb == 0u) continue;
             // split-reduce: each component's warp sum lands in one lane, which adds it to the surfel's gradient row (REDG.ADD.F32)
             const float tot = warp_split_reduce<NG>(g, lane);
-            if (my_comp >= 0 && tot != 0.0f) atomicAdd(my_dst + (size_t)s_id[j] * my_stride, tot);
+            if (my_comp >= 0 && tot != 0.0f) atomicAdd(my_dst + (size_t)st.id[sj] * my_stride, tot);
         }
         }
-        __syncthreads();
     }
 }
 
@@ -380,17 +399,22 @@ static int raster_backward_impl(const envgs_raster_args& a, const int* radii_in,
     ImageState im;
     ImageState::carve(img_buffer, W, H, &im);
     BinningState b;
-    BinningState::carve(binning_buffer, R, &b, sort_temp_bytes(R));
+    BinningState::carve(binning_buffer, R, &b, sort_temp_bytes(R), C);
     const int* radii = radii_in ? radii_in : g.internal_radii;
     const float focal_y = H / (2.0f * a.tan_fovy), focal_x = W / (2.0f * a.tan_fovx);
     const float* feat = a.colors_precomp ? a.colors_precomp : g.rgb;
 
     if (R > 0) {
+        constexpr size_t smem = 2 * sizeof(TileStage<C>) + 2 * sizeof(uint64_t);
+        static bool attr_set = false;
+        if (!attr_set) {
+            ENVGS_CUDA_TRY(cudaFuncSetAttribute(render_bwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
         ENVGS_TIMED("render_bwd", stream);
-        render_bwd_kernel<C><<<gx * gy, 256, 0, stream>>>(im.ranges, b.point_list, W, H, gx, a.background, g.rec,
-                                                          g.pixbox, feat, im.final_T, im.n_contrib, gr.dL_dout_color,
-                                                          gr.dL_dout_others, gr.dL_dtransMat, gr.dL_dmeans2D,
-                                                          gr.dL_dnormal, gr.dL_dopacity, gr.dL_dcolors);
+        render_bwd_kernel<C><<<gx * gy, 256, smem, stream>>>(im.ranges, b, W, H, gx, a.background, im.final_T, im.n_contrib,
+                                                             gr.dL_dout_color, gr.dL_dout_others, gr.dL_dtransMat, gr.dL_dmeans2D,
+                                                             gr.dL_dnormal, gr.dL_dopacity, gr.dL_dcolors);
         ENVGS_LAUNCH_CHECK("render_bwd", debug, stream);
     }
     ENVGS_TIMED("preprocess_bwd", stream);

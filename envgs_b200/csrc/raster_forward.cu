@@ -11,6 +11,7 @@
 #include <cub/cub.cuh>
 #include "raster_state.cuh"
 #include "glm_order.cuh"
+#include "tma.cuh"
 
 namespace envgs {
 
@@ -57,7 +58,7 @@ size_t ImageState::carve(char* base, int W, int H, ImageState* s) {
     obtain(p, g.ranges, tiles);
     return (size_t)(p - base) + 256;
 }
-size_t BinningState::carve(char* base, int N, BinningState* s, size_t sort_bytes) {
+size_t BinningState::carve(char* base, int N, BinningState* s, size_t sort_bytes, int C) {
     char* p = base;
     BinningState tmp;
     BinningState& g = s ? *s : tmp;
@@ -65,6 +66,11 @@ size_t BinningState::carve(char* base, int N, BinningState* s, size_t sort_bytes
     obtain(p, g.keys, (size_t)N);
     obtain(p, g.vals_unsorted, (size_t)N);
     obtain(p, g.point_list, (size_t)N);
+    g.cap = ((size_t)N + 8 + 63) / 64 * 64;
+    for (int k = 0; k < 4; k++) obtain(p, g.srec[k], g.cap);
+    obtain(p, g.sbox, g.cap);
+    obtain(p, g.sid, g.cap);
+    obtain(p, g.sfeat, (size_t)C * g.cap);
     obtain(p, g.sort_temp, sort_bytes);
     g.sort_temp_bytes = sort_bytes;
     return (size_t)(p - base) + 256;
@@ -286,6 +292,41 @@ __global__ void __launch_bounds__(256) tile_ranges_kernel(int L, const uint64_t*
     if (idx == L - 1) ranges[cur].y = L;
 }
 
+// Gather the per-instance render state into sorted structure-of-arrays order (BinningState::srec/sbox/sid/sfeat): one
+// 64-byte record gather + the feature row per instance, written back fully coalesced.  render_fwd and render_bwd then both
+// stream their tile's range with bulk asynchronous copies instead of each repeating the scattered gather.
+template <int C>
+__global__ void __launch_bounds__(256) gather_sorted_kernel(int N, const uint32_t* __restrict__ point_list,
+                                                            const float4* __restrict__ rec, const short4* __restrict__ pixbox,
+                                                            const float* __restrict__ features, BinningState b) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= N) return;
+    const int id = (int)point_list[k];
+#pragma unroll
+    for (int q = 0; q < 4; q++) b.srec[q][k] = rec[4 * (size_t)id + q];
+    b.sbox[k] = pixbox[id];
+    b.sid[k] = id;
+#pragma unroll
+    for (int ch = 0; ch < C; ch++) b.sfeat[(size_t)ch * b.cap + k] = features[(size_t)id * C + ch];
+}
+
+// one thread: arm the stage's barrier and issue the bulk copies of list entries [first, first + nb) (start rounded down /
+// count rounded up to multiples of 4 entries so every copy is 16-byte aligned; the consumer indexes with lead = first & 3)
+template <int C>
+__device__ __forceinline__ void issue_stage(TileStage<C>* st, uint64_t* bar, const BinningState& b, int first, int nb) {
+    const int a0 = first & ~3;
+    const uint32_t cnt = (uint32_t)(((first & 3) + nb + 3) & ~3);
+    mbar_arrive_expect_tx(bar, cnt * (uint32_t)(64 + 8 + 4 + 4 * C));
+    bulk_g2s(st->r0, b.srec[0] + a0, cnt * 16u, bar);
+    bulk_g2s(st->r1, b.srec[1] + a0, cnt * 16u, bar);
+    bulk_g2s(st->r2, b.srec[2] + a0, cnt * 16u, bar);
+    bulk_g2s(st->r3, b.srec[3] + a0, cnt * 16u, bar);
+    bulk_g2s(st->box, b.sbox + a0, cnt * 8u, bar);
+    bulk_g2s(st->id, b.sid + a0, cnt * 4u, bar);
+#pragma unroll
+    for (int ch = 0; ch < C; ch++) bulk_g2s(st->feat[ch], b.sfeat + (size_t)ch * b.cap + a0, cnt * 4u, bar);
+}
+
 // ------------------------------------------------------------------------------------------------------
 // render forward
 // ------------------------------------------------------------------------------------------------------
@@ -296,14 +337,13 @@ constexpr int RB = 256;   // batch size == CTA size
 
 template <int C>
 __global__ void __launch_bounds__(256) render_fwd_kernel(
-    const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int tiles_x,
-    const float4* __restrict__ rec, const short4* __restrict__ pixbox, const float* __restrict__ features,
-    const float* __restrict__ bg, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
-    float* __restrict__ out_color, float* __restrict__ out_others, float* __restrict__ out_weight) {
-    __shared__ float4 s_r0[RB], s_r1[RB], s_r2[RB], s_r3[RB];
-    __shared__ short4 s_box[RB];
-    __shared__ int s_id[RB];
-    __shared__ float s_feat[RB * C];
+    const uint2* __restrict__ ranges, const BinningState b, int W, int H, int tiles_x, const float* __restrict__ bg,
+    float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, float* __restrict__ out_color,
+    float* __restrict__ out_others, float* __restrict__ out_weight) {
+    // two staging buffers filled by bulk asynchronous copies (tma.cuh): batch i+1 is in flight while batch i is composited
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TileStage<C>* stages = reinterpret_cast<TileStage<C>*>(smem_raw);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + 2 * sizeof(TileStage<C>));
 
     const int tile = blockIdx.x;
     const int tx = tile % tiles_x, ty = tile / tiles_x;
@@ -320,6 +360,14 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(
     const int total = (int)(range.y - range.x);
     const int rounds = (total + RB - 1) / RB;
 
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_init_fence();
+    }
+    __syncthreads();
+    if (tid == 0 && rounds > 0) issue_stage<C>(&stages[0], &bars[0], b, (int)range.x, min(RB, total));
+
     bool done = !inside;
     float T = 1.0f;
     uint32_t last_contributor = 0, median_contributor = 0;
@@ -330,20 +378,16 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(
 
     int toDo = total;
     for (int i = 0; i < rounds; i++, toDo -= RB) {
-        if (__syncthreads_count(done) == RB) break;
-        int progress = i * RB + tid;
-        if (progress < total) {
-            int id = (int)point_list[range.x + progress];
-            s_id[tid] = id;
-            s_r0[tid] = rec[4 * (size_t)id + 0];
-            s_r1[tid] = rec[4 * (size_t)id + 1];
-            s_r2[tid] = rec[4 * (size_t)id + 2];
-            s_r3[tid] = rec[4 * (size_t)id + 3];
-            s_box[tid] = pixbox[id];
-#pragma unroll
-            for (int ch = 0; ch < C; ch++) s_feat[ch * RB + tid] = features[(size_t)id * C + ch];
+        // everyone is past batch i-1 here, so its buffer (the one batch i+1 goes into) may be overwritten
+        if (__syncthreads_count(done) == RB) {
+            if (tid == 0) mbar_wait(&bars[i & 1], (i >> 1) & 1);   // batch i is still in flight: it must land before the CTA exits
+            break;
         }
-        __syncthreads();
+        if (tid == 0 && i + 1 < rounds)
+            issue_stage<C>(&stages[(i + 1) & 1], &bars[(i + 1) & 1], b, (int)range.x + (i + 1) * RB, min(RB, toDo - RB));
+        mbar_wait(&bars[i & 1], (i >> 1) & 1);
+        const TileStage<C>& st = stages[i & 1];
+        const int lead = ((int)range.x + i * RB) & 3;
 
         const int nb = min(RB, toDo);
         bool warp_done = __all_sync(0xffffffffu, done);
@@ -354,7 +398,7 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(
         {
             const int jj = c0 + lane;
             if (jj < nb) {
-                const short4 bb = s_box[jj];
+                const short4 bb = st.box[lead + jj];
                 cand = !(bb.x > wx1 || bb.z < wx0 || bb.y > wy1 || bb.w < wy0);
             }
         }
@@ -362,7 +406,8 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(
         while (cmask && !warp_done) {
             const int j = c0 + __ffs(cmask) - 1;
             cmask &= cmask - 1;
-            const float4 r0 = s_r0[j], r1 = s_r1[j], r2 = s_r2[j];
+            const int sj = lead + j;
+            const float4 r0 = st.r0[sj], r1 = st.r1[sj], r2 = st.r2[sj];
             const float3 Tu = f3(r0.x, r0.y, r0.z), Tv = f3(r0.w, r1.x, r1.y), Tw = f3(r1.z, r1.w, r2.x);
             float w = 0.0f;
             bool contrib = false;
@@ -389,7 +434,7 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(
                             } else {
                                 contrib = true;
                                 w = alpha * T;
-                                const float4 r3 = s_r3[j];
+                                const float4 r3 = st.r3[sj];
                                 float A = 1.0f - T;
                                 float m = FAR_N / (FAR_N - NEAR_N) * (1.0f - px_div(NEAR_N, depth, px_rcp(depth)));
                                 distortion += (m * m * A + M2 - 2.0f * m * M1) * w;
@@ -400,7 +445,7 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(
                                 if (T > 0.5f) { median_depth = depth; median_contributor = pos; }
                                 N0 += r3.x * w; N1 += r3.y * w; N2 += r3.z * w;
 #pragma unroll
-                                for (int ch = 0; ch < C; ch++) Cacc[ch] += s_feat[ch * RB + j] * w;
+                                for (int ch = 0; ch < C; ch++) Cacc[ch] += st.feat[ch][sj] * w;
                                 T = test_T;
                                 last_contributor = pos;
                             }
@@ -411,12 +456,11 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(
             // per-surfel accumulated blend weight (forward.cu:420): warp-reduce, then one global reduction per (warp, surfel)
             if (__any_sync(0xffffffffu, contrib)) {
                 float ws = warp_sum(w);
-                if (lane == 0) atomicAdd(&out_weight[s_id[j]], ws);
+                if (lane == 0) atomicAdd(&out_weight[st.id[sj]], ws);
             }
             warp_done = __all_sync(0xffffffffu, done);
         }
         }
-        __syncthreads();
     }
 
     if (inside) {
@@ -492,11 +536,11 @@ static int raster_forward_impl(const envgs_raster_args& a, const envgs_raster_ou
     ENVGS_CUDA_TRY(cudaStreamSynchronize(stream));
 
     size_t sort_bytes = sort_temp_bytes(num_rendered);
-    size_t bin_bytes = BinningState::carve(nullptr, num_rendered, nullptr, sort_bytes);
+    size_t bin_bytes = BinningState::carve(nullptr, num_rendered, nullptr, sort_bytes, C);
     char* bin_ptr = (char*)binning_alloc(user, bin_bytes);
     if (!bin_ptr) { set_error("binning allocator returned NULL for %zu bytes", bin_bytes); return ENVGS_ERR_ALLOC; }
     BinningState b;
-    BinningState::carve(bin_ptr, num_rendered, &b, sort_bytes);
+    BinningState::carve(bin_ptr, num_rendered, &b, sort_bytes, C);
 
     ENVGS_CUDA_TRY(cudaMemsetAsync(im.ranges, 0, (size_t)gx * gy * sizeof(uint2), stream));
     if (num_rendered > 0) {
@@ -520,11 +564,21 @@ static int raster_forward_impl(const envgs_raster_args& a, const envgs_raster_ou
     }
 
     const float* feat = a.colors_precomp ? a.colors_precomp : g.rgb;
+    if (num_rendered > 0) {
+        ENVGS_TIMED("gather_sorted", stream);
+        gather_sorted_kernel<C><<<(num_rendered + 255) / 256, 256, 0, stream>>>(num_rendered, b.point_list, g.rec, g.pixbox, feat, b);
+        ENVGS_LAUNCH_CHECK("gather_sorted", debug, stream);
+    }
     {
+        constexpr size_t smem = 2 * sizeof(TileStage<C>) + 2 * sizeof(uint64_t);
+        static bool attr_set = false;   // > 48 KB of dynamic shared memory needs the opt-in once per kernel instance
+        if (!attr_set) {
+            ENVGS_CUDA_TRY(cudaFuncSetAttribute(render_fwd_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
         ENVGS_TIMED("render_fwd", stream);
-        render_fwd_kernel<C><<<gx * gy, 256, 0, stream>>>(im.ranges, b.point_list, W, H, gx, g.rec, g.pixbox, feat,
-                                                          a.background, im.final_T, im.n_contrib, o.out_color, o.out_others,
-                                                          o.out_weight);
+        render_fwd_kernel<C><<<gx * gy, 256, smem, stream>>>(im.ranges, b, W, H, gx, a.background, im.final_T, im.n_contrib,
+                                                             o.out_color, o.out_others, o.out_weight);
         ENVGS_LAUNCH_CHECK("render_fwd", debug, stream);
     }
     return num_rendered;

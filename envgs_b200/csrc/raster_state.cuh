@@ -45,9 +45,28 @@ struct BinningState {
     uint64_t* keys;           // N
     uint32_t* vals_unsorted;  // N
     uint32_t* point_list;     // N
+    // Per-instance render state in SORTED (tile, depth) order, structure-of-arrays: a tile's list is a contiguous index range
+    // of every array, so the tile kernels stage a 256-instance batch with a handful of bulk asynchronous copies
+    // (cp.async.bulk / UBLKCP, tma.cuh) instead of 256 scattered record gathers.  `cap` = N rounded up (+ slack so that a
+    // copy starting at an index rounded down to a multiple of 4 and ending rounded up never leaves the arrays).
+    float4* srec[4];          // cap each: the four float4 of the surfel record (raster_state.cuh header)
+    short4* sbox;             // cap
+    int32_t* sid;             // cap   surfel id (destination row of the gradient / weight reductions)
+    float* sfeat;             // C * cap, channel-major
+    size_t cap;
     char* sort_temp;
     size_t sort_temp_bytes;
-    static size_t carve(char* base, int N, BinningState* s, size_t sort_bytes);
+    static size_t carve(char* base, int N, BinningState* s, size_t sort_bytes, int C);
+};
+
+// shared-memory image of one staged batch (two of them are double-buffered); SB = 256 + up to 3 leading + 1..3 trailing
+constexpr int STAGE_SLOTS = 260;
+template <int C>
+struct TileStage {
+    float4 r0[STAGE_SLOTS], r1[STAGE_SLOTS], r2[STAGE_SLOTS], r3[STAGE_SLOTS];
+    short4 box[STAGE_SLOTS];
+    int32_t id[STAGE_SLOTS];
+    float feat[C][STAGE_SLOTS];
 };
 
 template <typename T>

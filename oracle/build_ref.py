@@ -42,9 +42,11 @@ def build_tracer(verbose: bool = False) -> dict:
         raise FileNotFoundError(f"{REF_TRACE} not present (the reference only exists in the build container)")
     bdir = os.path.join(OUT, "ref_trace")
     os.makedirs(bdir, exist_ok=True)
-    deps = [os.path.join(HERE, "ref_trace_driver.cu"), os.path.join(HERE, "optix_shim", "optix.h")]
+    deps = [os.path.join(HERE, "ref_trace_driver.cu"), os.path.join(HERE, "optix_shim", "optix.h"), os.path.join(HERE, "ref_trace_args.h")]
     built = {}
-    for src, flag, tag in (("forward.cu", "0", "fwd"), ("backward.cu", "1", "bwd")):
+    # "_nudge": the same forward program with every emulated hit distance moved by one fp32 ulp (conditioning experiment)
+    for src, flag, tag in (("forward.cu", "0", "fwd"), ("backward.cu", "1", "bwd"), ("forward.cu", "0", "fwd_nudge"),
+                           ("backward.cu", "1", "bwd_nudge")):
         so = os.path.join(bdir, f"libref_trace_{tag}.so")
         built[f"ref_trace_{tag}"] = so
         if os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(d) for d in deps):
@@ -52,10 +54,49 @@ def build_tracer(verbose: bool = False) -> dict:
         cmd = ["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-w",
                "-I", os.path.join(HERE, "optix_shim"), "-I", REF_TRACE,
                f'-DREF_TRACE_SOURCE="{os.path.join(REF_TRACE, src)}"', f"-DREF_TRACE_BACKWARD={flag}", deps[0], "-o", so]
+        if tag.endswith("nudge"):
+            cmd.insert(1, "-DOPTIX_SHIM_T_NUDGE=1")
         if verbose:
             print(" ".join(cmd))
         subprocess.run(cmd, check=True)
     return built
+
+
+def build_tracer_optix(verbose: bool = False) -> dict:
+    """The reference tracer's device programs under the REAL OptiX runtime: forward.ptx / backward.ptx generated from the
+    unmodified optix_tracer/{forward,backward}.cu (what optix_tracer/CMakeLists.txt's CUDA_PTX_COMPILATION does) plus the
+    C-ABI host driver oracle/ref_trace_optix_driver.cpp, which repeats the reference host code's OptiX calls
+    (optix_wrapper.cpp:33-215, trace_surfels.cpp:47-121, :233-311) against the vendored OptiX 7.7 headers.
+    Usable only where the driver's libnvoptix.so.1 can be loaded (/usr/local/nvidia/lib on this pool's GPU boxes, outside the
+    default loader path — oracle/ref_trace.py preloads it); otherwise the emulation build is the pin.
+    (The reference's own pybind extension — trace_surfels.cpp, ext.cpp, optix_wrapper.cpp, common.cpp — also compiles here
+    with torch.utils.cpp_extension, but its OptiXStateWrapper() segfaults on this image; profiles/round2_optix_probe.txt.)"""
+    import subprocess
+    top = os.path.dirname(REF_TRACE)
+    if not os.path.isdir(top):
+        raise FileNotFoundError(top)
+    bdir = os.path.join(OUT, "ref_trace_optix")
+    os.makedirs(bdir, exist_ok=True)
+    inc = os.path.join(top, "third_party", "optix", "include")
+    so = os.path.join(bdir, "libref_trace_optix.so")
+    src = os.path.join(HERE, "ref_trace_optix_driver.cpp")
+    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-w", "-I", inc, "-I", REF_TRACE, "-I", "/usr/local/cuda/include",
+                        "-I", HERE, src, "-o", so, "-L/usr/local/cuda/lib64", "-lcudart", "-ldl"], check=True)
+    probe_src = os.path.join(HERE, "optix_probe", "optix_min_probe.cpp")
+    probe = os.path.join(bdir, "optix_min_probe")
+    if os.path.exists(probe_src) and not os.path.exists(probe):
+        subprocess.run(["g++", "-O1", "-std=c++17", "-w", "-I", inc, "-I", "/usr/local/cuda/include", probe_src, "-o", probe,
+                        "-L/usr/local/cuda/lib64", "-lcudart", "-ldl"], check=True)
+    for arch in ("compute_100", "compute_80"):    # two PTX targets: OptiX JIT-compiles whichever its parser accepts
+        pdir = os.path.join(bdir, "ptx_" + arch)
+        os.makedirs(pdir, exist_ok=True)
+        for name in ("forward", "backward"):
+            ptx = os.path.join(pdir, name + ".ptx")
+            if not os.path.exists(ptx):
+                subprocess.run(["nvcc", "-ptx", "-O3", "-std=c++17", "-arch=" + arch, "-w", "-I", inc, "-I", REF_TRACE,
+                                os.path.join(REF_TRACE, name + ".cu"), "-o", ptx], check=True)
+    return {"ref_trace_optix": so}
 
 
 def build(verbose: bool = False) -> dict:
@@ -82,6 +123,10 @@ def build(verbose: bool = False) -> dict:
             build_directory=bdir, verbose=verbose, is_python_module=False)
         built[name] = so
     built.update(build_tracer(verbose))
+    try:
+        built.update(build_tracer_optix(verbose))
+    except Exception as ex:   # optional: only a second, stronger pin and a timing baseline
+        print(f"[build_ref] real-OptiX tracer build skipped: {ex}")
     return built
 
 

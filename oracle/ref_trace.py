@@ -31,6 +31,8 @@ class _Args(ctypes.Structure):
 
 
 _LIBS: dict = {}
+OPTIX_OUT = os.path.join(os.path.dirname(OUT), "ref_trace_optix")
+_OPTIX: dict = {}
 
 
 def available() -> bool:
@@ -45,9 +47,97 @@ def _lib(kind: str):
         L = ctypes.CDLL(path)
         L.ref_trace_launch.argtypes = [ctypes.POINTER(_Args), ctypes.c_void_p]
         L.ref_trace_launch.restype = ctypes.c_int
-        assert L.ref_trace_is_backward() == (1 if kind == "bwd" else 0)
+        assert L.ref_trace_is_backward() == (1 if kind.startswith("bwd") else 0)
         _LIBS[kind] = L
     return _LIBS[kind]
+
+
+# ---- real OptiX backend (oracle/ref_trace_optix_driver.cpp) -----------------------------------------------------------
+def _optix_init():
+    if _OPTIX:
+        return
+    try:
+        import glob
+        so = os.path.join(OPTIX_OUT, "libref_trace_optix.so")
+        if not os.path.exists(so):
+            raise FileNotFoundError(so)
+        # libnvoptix and the RTX core it dlopens by name sit outside the default loader path on this pool's boxes
+        # (/usr/local/nvidia/lib): preload both by absolute path so the later dlopen-by-soname calls resolve
+        for dep in sorted(glob.glob("/usr/local/nvidia/lib*/libnvidia-rtcore.so.*")) + sorted(glob.glob("/usr/local/nvidia/lib*/libnvidia-ptxjitcompiler.so.*")):
+            try:
+                ctypes.CDLL(dep, mode=ctypes.RTLD_GLOBAL)
+            except OSError:
+                pass
+        loaded = None
+        for c in ["libnvoptix.so.1"] + sorted(glob.glob("/usr/local/nvidia/lib*/libnvoptix.so.1")) + \
+                sorted(glob.glob("/usr/lib/x86_64-linux-gnu/libnvoptix.so.1")):
+            try:
+                ctypes.CDLL(c, mode=ctypes.RTLD_GLOBAL)
+                loaded = c
+                break
+            except OSError:
+                continue
+        if loaded is None:
+            raise OSError("libnvoptix.so.1 not loadable")
+        L = ctypes.CDLL(so)
+        L.ref_optix_last_error.restype = ctypes.c_char_p
+        L.ref_optix_create.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int]
+        L.ref_optix_build.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        L.ref_optix_launch.argtypes = [ctypes.POINTER(_Args), ctypes.c_int, ctypes.c_void_p]
+        last = ""
+        for arch in ("compute_100", "compute_80"):
+            d = os.path.join(OPTIX_OUT, "ptx_" + arch)
+            if L.ref_optix_create(os.path.join(d, "forward.ptx").encode(), os.path.join(d, "backward.ptx").encode(), 0) == 0:
+                _OPTIX.update(lib=L, ptx=arch, nvoptix=loaded)
+                return
+            last = L.ref_optix_last_error().decode()
+        raise RuntimeError(f"OptiX pipeline creation failed: {last}")
+    except Exception as ex:   # noqa: BLE001
+        _OPTIX["err"] = f"{type(ex).__name__}: {ex}"
+
+
+def optix_available() -> bool:
+    if not torch.cuda.is_available():
+        return False
+    _optix_init()
+    return "lib" in _OPTIX
+
+
+def optix_info() -> dict:
+    _optix_init()
+    return {k: _OPTIX.get(k) for k in ("ptx", "nvoptix", "err")}
+
+
+def optix_build(vertices: torch.Tensor, triangles: torch.Tensor) -> None:
+    """optixAccelBuild of the quad triangles (trace_surfels.cpp:47-121); the handle lives in the driver."""
+    _optix_init()
+    L = _OPTIX["lib"]
+    v, t = vertices.detach().contiguous().float(), triangles.contiguous().int()
+    with torch.cuda.device(v.device):
+        rc = L.ref_optix_build(v.data_ptr(), v.shape[0], t.data_ptr(), t.shape[0], ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        torch.cuda.current_stream().synchronize()
+    if rc != 0:
+        raise RuntimeError("reference OptiX build failed: " + L.ref_optix_last_error().decode())
+    _OPTIX["built_for"] = (v.data_ptr(), v.shape[0])
+
+
+def _launch(backend: str, backward: bool, a, kw):
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    if backend == "optix":
+        _optix_init()
+        if "lib" not in _OPTIX:
+            raise RuntimeError("real-OptiX reference backend unavailable: " + _OPTIX.get("err", ""))
+        if kw.get("rebuild", True):
+            optix_build(kw["vertices"], kw["triangles"])
+        L = _OPTIX["lib"]
+        rc = L.ref_optix_launch(ctypes.byref(a), int(backward), stream)
+        if rc != 0:
+            raise RuntimeError("reference OptiX launch failed: " + L.ref_optix_last_error().decode())
+        return
+    kind = ("bwd" if backward else "fwd") + ("_nudge" if backend == "emulation_nudge" else "")
+    rc = _lib(kind).ref_trace_launch(ctypes.byref(a), stream)
+    if rc != 0:
+        raise RuntimeError(f"reference tracer {kind} failed: {rc}")
 
 
 def _ptr(t):
@@ -56,7 +146,7 @@ def _ptr(t):
 
 def _common(a, keep, *, ray_o, ray_d, vertices, triangles, bg, means3D, shs, degree, colors_precomp, others_precomp, opacities,
             scales, scale_modifier, rotations, viewmatrix, projmatrix, campos, start_from_first, max_trace_depth,
-            specular_threshold):
+            specular_threshold, rebuild=True):
     f32 = lambda t: None if t is None else t.detach().contiguous().float()
     ray_o, ray_d, vertices, bg, means3D, shs, colors_precomp, others_precomp, opacities, scales, rotations, viewmatrix, \
         projmatrix, campos = map(f32, (ray_o, ray_d, vertices, bg, means3D, shs, colors_precomp, others_precomp, opacities,
@@ -76,8 +166,9 @@ def _common(a, keep, *, ray_o, ray_d, vertices, triangles, bg, means3D, shs, deg
     return a.P, a.H, a.W, a.M
 
 
-def trace_forward(*, training=True, **kw):
-    """-> dict(rgb, dpt, acc, norm, dist(H,W,3), aux, mid, wet) of CUDA tensors."""
+def trace_forward(*, training=True, backend="emulation", **kw):
+    """-> dict(rgb, dpt, acc, norm, dist(H,W,3), aux, mid, wet) of CUDA tensors.  backend: "emulation" (brute-force OptiX
+    emulation), "emulation_nudge" (same, hit distances moved by one ulp), "optix" (the driver's real OptiX runtime)."""
     a, keep = _Args(), []
     P, H, W, M = _common(a, keep, **kw)
     dev = kw["means3D"].device
@@ -89,13 +180,11 @@ def trace_forward(*, training=True, **kw):
         _ptr(out[k]) for k in ("rgb", "dpt", "acc", "norm", "dist", "aux", "mid"))
     a.a_weights = _ptr(out["wet"]) if training else None
     with torch.cuda.device(dev):
-        rc = _lib("fwd").ref_trace_launch(ctypes.byref(a), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
-    if rc != 0:
-        raise RuntimeError(f"reference tracer forward failed: {rc}")
+        _launch(backend, False, a, dict(kw, vertices=keep[2], triangles=keep[3]))
     return out
 
 
-def trace_backward(fwd: dict, grads: dict, **kw):
+def trace_backward(fwd: dict, grads: dict, backend="emulation", **kw):
     """fwd = trace_forward's result; grads = dict(rgb, dpt, acc, norm, dist(H,W,1), aux) upstream gradients.
     -> dict(g_ray_o, g_ray_d, g_means, g_shs, g_colors, g_others, g_opac, g_scales, g_rots, g_transMat)."""
     a, keep = _Args(), []
@@ -113,7 +202,5 @@ def trace_backward(fwd: dict, grads: dict, **kw):
         a.dL_drotations, a.dL_dtransMat = (ctypes.c_void_p(out[k].data_ptr()) for k in (
             "g_ray_o", "g_ray_d", "g_means", "g_shs", "g_colors", "g_others", "g_opac", "g_scales", "g_rots", "g_transMat"))
     with torch.cuda.device(dev):
-        rc = _lib("bwd").ref_trace_launch(ctypes.byref(a), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
-    if rc != 0:
-        raise RuntimeError(f"reference tracer backward failed: {rc}")
+        _launch(backend, True, a, dict(kw, vertices=keep[2], triangles=keep[3], rebuild=False))
     return out

@@ -61,6 +61,7 @@ class TraceOut:
 # ~7e-5 relative in alpha (tools/trace_diag.py, profiles/round2_parity_experiments.md): the reference's own fp32 result
 # and any other fp32 evaluation (including real OptiX's hit distance vs the emulation's) may land on different sides.
 BORDER_REL = 3e-4
+BORDER_REL_LATER = 1.5e-3   # later segments start from the previous segment's fp32 depth/normal: their rays carry its noise too
 
 
 def _chunk_restart_keep(tk: torch.Tensor, hk: torch.Tensor) -> torch.Tensor:
@@ -85,7 +86,7 @@ def _chunk_restart_keep(tk: torch.Tensor, hk: torch.Tensor) -> torch.Tensor:
 
 
 def _segment(ray_o, ray_d, pix, active, means, scales, rotations, opacities, shs, sh_degree, colors, others, campos, bg,
-             first, projmatrix, W, H, scale_modifier, max_hits, ray_chunk):
+             first, projmatrix, W, H, scale_modifier, max_hits, ray_chunk, border_rel=BORDER_REL):
     """Trace one segment for R rays.  Returns C(R,3), D, A, N(R,3), dist, M1, M2, O(R,2), wet(P)."""
     dt = means.dtype
     dev = means.device
@@ -116,7 +117,7 @@ def _segment(ray_o, ray_d, pix, active, means, scales, rotations, opacities, shs
             v = ((x * tv[None]).sum(-1) - (means * tv).sum(-1)[None]) / scales[None, :, 1]
             hit = (q != 0) & (t > 0) & (t < 1e16) & (u.abs() <= 3) & (v.abs() <= 3) & act[:, None] & torch.isfinite(t)
             emax = torch.maximum(u.abs(), v.abs())
-            near_edge = ((q != 0) & (t > 0) & act[:, None] & torch.isfinite(t) & ((emax - 3.0).abs() <= 3.0 * BORDER_REL)).any(1)
+            near_edge = ((q != 0) & (t > 0) & act[:, None] & torch.isfinite(t) & ((emax - 3.0).abs() <= 3.0 * border_rel)).any(1)
             tkey = torch.where(hit, t, torch.full_like(t, float("inf")))
             k = min(max_hits, P)
             tk, ik = torch.topk(tkey, k, dim=1, largest=False, sorted=True)       # (r,k)
@@ -165,9 +166,9 @@ def _segment(ray_o, ray_d, pix, active, means, scales, rotations, opacities, shs
         cand = hk & cos_ok & (~skip_xy) & (cmd >= min_depth) & (power <= 0) & (alpha >= 1.0 / 255.0)
         with torch.no_grad():
             thr = 1.0 / 255.0
-            nb_ = hk & cos_ok & (((alpha - thr).abs() <= BORDER_REL * thr) | ((cmd - min_depth).abs() <= BORDER_REL * min_depth))
+            nb_ = hk & cos_ok & (((alpha - thr).abs() <= border_rel * thr) | ((cmd - min_depth).abs() <= border_rel * min_depth))
             if first:
-                nb_ = nb_ | (hk & ((rho3d - rho2d).abs() <= BORDER_REL * rho2d.abs()))
+                nb_ = nb_ | (hk & ((rho3d - rho2d).abs() <= border_rel * rho2d.abs()))
         one_m = torch.where(cand, 1.0 - alpha, torch.ones_like(alpha))
         Tincl = torch.cumprod(one_m, dim=1)
         Tbefore = torch.cat([torch.ones(r, 1, dtype=dt, device=dev), Tincl[:, :-1]], dim=1)
@@ -232,7 +233,8 @@ def trace(ray_o, ray_d, means3D, opacities, scales, rotations, shs=None, colors_
         first = (i == 0) and start_from_first
         Cc, D, A, Nn, dist, M1, M2, O, wet, brd = _segment(o, d, pix, active, means3D, scales, rotations, opacities, shs, sh_degree,
                                                       colors_precomp, others_precomp, campos, bgv, first, projmatrix, W, H,
-                                                      scale_modifier, max_hits, ray_chunk)
+                                                      scale_modifier, max_hits, ray_chunk,
+                                                      BORDER_REL if i == 0 else BORDER_REL_LATER)
         wet_total = wet_total + wet
         border_total = brd if i == 0 else (border_total | (brd & active))
         a = active.to(dt)

@@ -234,9 +234,11 @@ def run_oracle_trace(env, cam, ray_o, ray_d, *, use_sh=True, others=False, start
 
 
 def run_reference_trace(env, cam, ray_o, ray_d, *, use_sh=True, others=False, start_from_first=False, max_trace_depth=0,
-                        specular_threshold=0.0, grads=None, device="cuda", training=True, bg=None):
-    """The UNMODIFIED reference tracer programs (oracle/_ref/ref_trace, OptiX traversal emulated by brute force) on the
-    same inputs as run_cuda_trace, wrapped the way diff_surfel_tracing/__init__.py:51-204 wraps them."""
+                        specular_threshold=0.0, grads=None, device="cuda", training=True, bg=None, backend="emulation"):
+    """The UNMODIFIED reference tracer programs on the same inputs as run_cuda_trace, wrapped the way
+    diff_surfel_tracing/__init__.py:51-204 wraps them.  backend "emulation": oracle/_ref/ref_trace (OptiX traversal emulated
+    by brute force); "emulation_nudge": same with every hit distance moved by one ulp; "optix": the real OptiX runtime
+    (oracle/_ref/ref_trace_optix; needs the driver's libnvoptix)."""
     from oracle import ref_trace as RT
     dev = torch.device(device)
     bg = torch.zeros(3) if bg is None else bg
@@ -253,14 +255,14 @@ def run_reference_trace(env, cam, ray_o, ray_d, *, use_sh=True, others=False, st
               colors_precomp=colors, others_precomp=oth, opacities=opac, scales=scales, scale_modifier=1.0, rotations=rots,
               viewmatrix=cam.viewmatrix.to(dev), projmatrix=cam.projmatrix.to(dev), campos=cam.campos.to(dev),
               start_from_first=start_from_first, max_trace_depth=max_trace_depth, specular_threshold=specular_threshold)
-    fwd = RT.trace_forward(training=training, **kw)
+    fwd = RT.trace_forward(training=training, backend=backend, **kw)
     out = {k: fwd[k].cpu() for k in ("rgb", "dpt", "acc", "norm", "aux", "mid", "wet")}
     out["dist"] = fwd["dist"][..., :1].cpu()
     if grads is not None:
         H, W = ray_o.shape[:2]
         up = dict(grads)
         up.setdefault("dist", torch.zeros(H, W, 1))
-        bw = RT.trace_backward(fwd, up, **kw)
+        bw = RT.trace_backward(fwd, up, backend=backend, **kw)
         out.update(g_means=bw["g_means"].cpu(), g_opac=bw["g_opac"].cpu(), g_scales=bw["g_scales"].cpu(), g_rots=bw["g_rots"].cpu(),
                    g_ray_o=bw["g_ray_o"].cpu(), g_ray_d=bw["g_ray_d"].cpu())
         out["g_grads3D"] = out["g_means"] * (env.means - cam.campos[None]).norm(dim=-1, keepdim=True) / 2

@@ -84,6 +84,9 @@ def test_tracer_matches_reference_at_baseline_env_size(built_lib, P_env, two_seg
               norm=Hh.upstream((H, W, 3), 23), aux=Hh.upstream((H, W, 2), 24))
     kw = dict(use_sh=True, others=True, max_trace_depth=1, specular_threshold=0.01) if two_segments else dict(use_sh=True)
     ref = Hh.run_reference_trace(env, cam, ro, rd, grads=up, **kw)
+    # conditioning floor: 40-mm surfels 8-20 units away put ~1e-4 of fp32 noise into alpha already inside the reference, and a
+    # second segment starts from the first one's accumulated depth, amplifying it by 1/scale
+    noise = Hh.run_reference_trace(env, cam, ro, rd, grads=up, backend="emulation_nudge", **kw)
     cu = Hh.run_cuda_trace(env, cam, ro, rd, grads=up, **kw)
     border = Hh.run_oracle_trace(env, cam, ro, rd, grads=None, device="cuda", max_hits=256, ray_chunk=128, **kw)["border"]
-    check_trace_against_golden(cu, ref, kw, border)
+    check_trace_against_golden(cu, ref, kw, border, noise=noise)

@@ -63,27 +63,39 @@ def trace_mid_mask(gold, kw):
 BORDER_TOL = 2e-2     # a flipped borderline hit moves a ray by at most its own weight (alpha*T <= 0.011 at the quad edge)
 
 
-def check_trace_against_golden(out, gold, kw, border, img_tol=TRACE_IMG_TOL, grad_tol=TRACE_GRAD_TOL):
+def check_trace_against_golden(out, gold, kw, border, noise=None, img_tol=TRACE_IMG_TOL, grad_tol=TRACE_GRAD_TOL):
     """`border` (H,W) bool from the fp64 oracle: rays on which a discrete per-hit decision (alpha >= 1/255, quad edge, min
     depth) lies within fp32 noise of its threshold (oracle/trace_oracle.py BORDER_REL) — there either outcome is a correct
-    fp32 evaluation, so those rays get the one-flipped-hit bound instead of 1e-4.  Everything else is strict."""
+    fp32 evaluation, so those rays get the one-flipped-hit bound instead of 1e-4.  Everything else is strict.
+    `noise` (large live scenes only): the reference's own outputs re-computed with every OptiX hit distance moved by ONE
+    fp32 ulp (oracle/optix_shim/optix.h OPTIX_SHIM_T_NUDGE).  Whatever that changes is below the resolution of the reference
+    itself — a different but equally valid intersector (real OptiX) moves its results by as much — so the bound becomes
+    max(1e-4, 4 x that) there.  It is never used for the committed golden cases."""
     assert float(border.float().mean()) <= 0.3
     strict = ~border
     for k in ("rgb", "dpt", "acc", "norm", "aux", "dist"):
         scale = max(1.0, float(gold[k].abs().max()))
         d = (out[k] - gold[k]).abs().amax(-1)
-        assert float(d[strict].max()) <= img_tol * scale, Hh.image_report(k, out[k], gold[k], img_tol * scale)
+        tol = img_tol * scale
+        if noise is not None:
+            nz = (noise[k] - gold[k]).abs().amax(-1)
+            tol = max(tol, 4.0 * float(nz[strict].max()))
+            assert float(d[strict].mean()) <= 1e-5 * scale + 4.0 * float(nz[strict].mean()), Hh.image_report(k, out[k], gold[k], tol)
+        assert float(d[strict].max()) <= tol, Hh.image_report(k, out[k], gold[k], tol) + f" (tolerance {tol:.3e})"
         if k != "dpt" and kw.get("max_trace_depth", 0) == 0:
-            assert float(d.max()) <= BORDER_TOL * scale, Hh.image_report(k, out[k], gold[k], img_tol * scale)
-    _, ran1 = trace_mid_mask(gold, kw)
-    a, b = out["mid"].clone(), gold["mid"].clone()
-    a[..., 16:][~ran1] = 0
-    b[..., 16:][~ran1] = 0
-    scale = max(1.0, float(b.abs().max()))
-    assert float((a - b).abs().amax(-1)[strict].max()) <= img_tol * scale * 10, Hh.image_report("mid", a, b)   # segment-2 origins: 1e-3
-    assert Hh.rel_l2(out["wet"].reshape(-1), gold["wet"].reshape(-1)) <= 1e-4
+            assert float(d.max()) <= max(tol, BORDER_TOL * scale), Hh.image_report(k, out[k], gold[k], img_tol * scale)
+    if noise is None:
+        _, ran1 = trace_mid_mask(gold, kw)
+        a, b = out["mid"].clone(), gold["mid"].clone()
+        a[..., 16:][~ran1] = 0
+        b[..., 16:][~ran1] = 0
+        scale = max(1.0, float(b.abs().max()))
+        assert float((a - b).abs().amax(-1)[strict].max()) <= img_tol * scale * 10, Hh.image_report("mid", a, b)   # segment-2 origins: 1e-3
+    wet_tol = 1e-4 if noise is None else max(1e-4, 4.0 * Hh.rel_l2(noise["wet"].reshape(-1), gold["wet"].reshape(-1)))
+    assert Hh.rel_l2(out["wet"].reshape(-1), gold["wet"].reshape(-1)) <= wet_tol
     for k in [k for k in gold if k.startswith("g_")]:
-        assert Hh.rel_l2(out[k], gold[k]) <= grad_tol, f"{k}: rel L2 {Hh.rel_l2(out[k], gold[k]):.3e}"
+        tol = grad_tol if noise is None else max(grad_tol, 4.0 * Hh.rel_l2(noise[k], gold[k]))
+        assert Hh.rel_l2(out[k], gold[k]) <= tol, f"{k}: rel L2 {Hh.rel_l2(out[k], gold[k]):.3e} (tolerance {tol:.3e})"
 
 
 def oracle_for_trace_case(name, grads=True):
