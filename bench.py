@@ -44,6 +44,9 @@ def parse_args():
     ap.add_argument("--workload", default="config3", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip the in-process timing of the reference GPU operators")
+    ap.add_argument("--reference-device", default="auto", choices=["auto", "cpu"],
+                    help="--impl reference: 'auto' runs the real reference on the GPU when it can (else the CPU port); 'cpu' forces the CPU port")
     return ap.parse_args()
 
 
@@ -176,9 +179,84 @@ def cpu_sample(workload: str, n_tiles: int = 24, n_rays: int = 48, seed: int = 0
                       f"brute-force traced fwd+bwd over {Pe} env surfels; fp32 torch oracle, {threads} threads; scaled to a full view"}
 
 
+def reference_gpu_renderer(Pb, Pe, H, W, dev):
+    """The per-view path on the UNMODIFIED reference operators (oracle/ref_ops.py: the reference rasterizer extension built
+    for sm_100a + its tracer device programs under the driver's real OptiX) with the reference's own PyTorch glue
+    (EnvGSRenderer fused_* = False mirrors envgs_sampler.py / gaussian2d_utils.py line by line).  None of this repository's
+    kernels run on this path."""
+    from envgs_b200 import scene
+    from envgs_b200.pipeline import EnvGSRenderer
+    from oracle import ref_ops
+    s0 = 0.005 if H >= 1080 else 0.005 * 1080 / H
+    base = scene.make_base_set(Pb, seed=0, s0=s0)
+    env = scene.make_env_set(Pe, seed=1, s0=s0) if Pe > 0 else None
+    return EnvGSRenderer(base, env, device=dev, fused_features=False, fused_glue=False, rasterizer_cls=ref_ops.RefGaussianRasterizer,
+                         tracer=ref_ops.RefSurfelTracer() if Pe > 0 else None)
+
+
+def run_reference_arm_gpu(args) -> bool:
+    """`--impl reference` when the real reference can run on this box's GPU: full steps of the same workload (render +
+    backward + torch Adam, as the reference's trainer does), timed like the main arm.  Returns False if unavailable."""
+    if args.reference_device == "cpu" or not torch.cuda.is_available():
+        return False
+    from oracle import ref_ops
+    ok, why = ref_ops.available()
+    if not ok:
+        print(f"[bench] real reference not runnable on the GPU here ({why}); falling back to the CPU port", file=sys.stderr)
+        return False
+    from envgs_b200 import scene
+    Pb, Pe, H, W = WORKLOADS[args.workload]
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    renderer = reference_gpu_renderer(Pb, Pe, H, W, dev)
+    opt = torch.optim.Adam(renderer.parameters(), lr=1e-6, eps=1e-15)
+    cams = [c.to(dev) for c in scene.ring_cameras(138, H, W, seed=2)]
+    target = torch.rand(H, W, 3, generator=torch.Generator().manual_seed(3)).to(dev)
+
+    def step(k):
+        opt.zero_grad(set_to_none=True)
+        out = renderer(cams[k % len(cams)], target)
+        loss = renderer.loss(out, target)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for k in range(args.warmup):
+        step(k)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.warmup, args.warmup + args.steps):
+        step(k)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    v = H * W / (ms * 1e-3) / 1e6
+    from oracle import ref_trace as RT
+    sample = (f"full steps of the same workload on the UNMODIFIED reference operators on this box's GPU 0 (the reference has no CPU "
+              f"path, SURVEY.md §8d): diff-surfel-rasterization-wet-ch05 CUDA extension built for sm_100a + diff-surfel-tracing device "
+              f"programs under the driver's OptiX runtime ({RT.optix_info().get('nvoptix')}, PTX {RT.optix_info().get('ptx')}), reference "
+              f"PyTorch glue, torch.optim.Adam; 1 view/step")
+    line = {
+        "impl": "reference", "metric": "render Mpix/s (fwd+bwd, rasterize+trace)", "value": round(v, 4), "unit": "Mpix/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {Pb} base + {Pe} env surfels, SH deg 3, {W}x{H}, 1-bounce reflection trace, fwd+bwd + "
+                               f"OptiX GAS rebuild + Adam, 1 view/step on 1 GPU (the reference has no multi-GPU path)",
+                   "reference_device": "gpu"},
+        "cpu_baseline": {"value": round(v, 4), "unit": "Mpix/s", "cores": 0, "kind": "reference", "sample": sample},
+        "e2e": {"value": round(v, 4), "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return True
+
+
 def run_reference_arm(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
+        return
+    if run_reference_arm_gpu(args):
         return
     Pb, Pe, H, W = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
@@ -196,7 +274,8 @@ def run_reference_arm(args) -> None:
         "impl": "reference", "metric": "render Mpix/s (fwd+bwd, rasterize+trace)", "value": v, "unit": "Mpix/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {Pb} base + {Pe} env surfels, {W}x{H}, fwd+bwd, bounded CPU sample per step"},
+        "config": {"workload": f"{args.workload}: {Pb} base + {Pe} env surfels, {W}x{H}, fwd+bwd, bounded CPU sample per step",
+                   "reference_device": "cpu"},
         "cpu_baseline": {"value": v, "unit": "Mpix/s", "cores": min(cores, 32), "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -311,44 +390,77 @@ def main():
     h2d = packs[0].numel() * 4 + target_host.numel() * 4
     d2h = 4
 
-    # ---- per-kernel device times + roofline of render_fwd (rank 0, separate short run so events do not perturb the numbers) ----
-    roofline, kernels = None, None
+    # ---- per-kernel device times + rooflines (rank 0, separate short run so the events do not perturb the timed region) ----
+    roofline, rooflines, kernels, ref_gpu = None, None, None, None
     if rank == 0 and not args.no_profile:
+        import ctypes
+        have_env = Pe > 0
         _lib.profile_enable(True)
         nprof = 3
-        stats = []
+        P_v, P_hit = 0, 0
         for s in range(nprof):
             cam = dev_cams[s % len(dev_cams)]
             trainer.flat.zero_grad()
             out = renderer(cam, target_dev)
             renderer.loss(out, target_dev).backward()
             torch.cuda.synchronize()
-            stats.append((int((out["radii"] > 0).sum()),))
+            P_v = int((out["radii"] > 0).sum())
+            if have_env:
+                P_hit = int((out["env"]["wet"] > 0).sum())
         rep = _lib.profile_report()
         _lib.profile_enable(False)
         kernels = {k: round(v[1] / v[0], 4) for k, v in rep.items()}
-        # num_rendered of the last frame: read from the autograd context is awkward; recompute cheaply from the profile run
+        Hh = 0
+        if have_env:                                # one extra forward with the (slower) counting traversal, outside the timed profile
+            _lib.lib().envgs_debug_trace_stats(renderer.tracer.optix_context.handle, 1, None)
+            with torch.no_grad():
+                renderer(dev_cams[(nprof - 1) % len(dev_cams)], target_dev)
+            torch.cuda.synchronize()
+            buf = (ctypes.c_uint64 * 8)()
+            _lib.lib().envgs_debug_trace_stats(renderer.tracer.optix_context.handle, 0, buf)
+            Hh = int(buf[3])                        # quad hits found by the traversal of one view (>= the composited hits)
         N = renderer_last_num_rendered(renderer, dev_cams[(nprof - 1) % len(dev_cams)])
-        P_v = stats[-1][0]
-        C = 5
-        alg_bytes = (64 + 4 * C) * N + (48 + 4 * C) * H * W + 4 * P_v      # SURVEY.md §8d render_fwd
+        C, S, R = 5, 16, H * W
         peak, peak_src = measured_peaks()
-        t_ms = kernels.get("render_fwd")
-        if t_ms:
-            ach = alg_bytes / (t_ms * 1e-3) / 1e9
-            traffic, traffic_src = None, None
-            try:                                    # DRAM bytes of this kernel from the committed ncu --set full capture
-                with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-                    tj = json.load(f).get(args.workload)
-                if tj and tj.get("kernel") == "render_fwd_kernel<5>":
-                    traffic, traffic_src = int(tj["traffic"]), tj.get("source")
-            except Exception:
-                pass
-            roofline = {"kernel": "render_fwd_kernel<5>", "bound": "hbm", "achieved": round(ach, 2), "peak": peak, "unit": "GB/s",
-                        "frac": round(ach / peak, 4), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                        "algorithmic_bytes": alg_bytes,
-                        "launch_ms": t_ms, "num_rendered": N, "visible_surfels": P_v,
-                        "note": "render_fwd is fp32-issue bound, not HBM bound (SURVEY.md §8d); see DESIGN.md"}
+        try:
+            with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+                traffic_db = json.load(f).get(args.workload, {})
+        except Exception:
+            traffic_db = {}
+        # SURVEY.md §8d algorithmic bytes per view; "kernels" lists the profile entries whose time the bytes are set against
+        groups = {
+            "render_fwd": dict(kernel="render_fwd_kernel<5>", kernels=["render_fwd"], bytes=(64 + 4 * C) * N + (48 + 4 * C) * H * W + 4 * P_v),
+            "render_bwd": dict(kernel="render_bwd_kernel<5>", kernels=["render_bwd"],
+                               bytes=(64 + 4 * C) * N + (48 + 4 * C) * H * W + (60 + 4 * C) * P_v),
+        }
+        if have_env:
+            groups["trace_fwd"] = dict(kernel="traverse_kernel + shade_fwd_kernel (+ overflow fallback)",
+                                       kernels=["trace_traverse", "trace_class_lists", "trace_shade_fwd", "trace_fwd_fallback"],
+                                       bytes=24 * R + (52 + 64 * 1) * R + (44 + 12 * S) * Hh)
+            groups["trace_bwd"] = dict(kernel="shade_bwd_kernel (+ overflow fallback)", kernels=["trace_shade_bwd", "trace_bwd_fallback"],
+                                       bytes=(24 + 52 + 64 * 1 + 44 + 24) * R + (40 + 12 * S) * Hh + (40 + 12 * S) * P_hit)
+        rooflines = []
+        for name, gdef in groups.items():
+            t_ms = sum(kernels.get(k, 0.0) for k in gdef["kernels"])
+            if t_ms <= 0:
+                continue
+            ach = gdef["bytes"] / (t_ms * 1e-3) / 1e9
+            tj = traffic_db.get(name, {})
+            rooflines.append({"name": name, "kernel": gdef["kernel"], "bound": "hbm", "achieved": round(ach, 2), "peak": peak, "unit": "GB/s",
+                              "frac": round(ach / peak, 4), "traffic": tj.get("traffic"), "traffic_source": tj.get("source"),
+                              "peak_source": peak_src, "algorithmic_bytes": int(gdef["bytes"]), "launch_ms": round(t_ms, 4)})
+        if rooflines:
+            roofline = dict(max(rooflines, key=lambda r: r["launch_ms"]))      # the dominant kernel group of the step
+            roofline.update(num_rendered=N, visible_surfels=P_v, rays=R, composited_hits=Hh, env_surfels_hit=P_hit,
+                            note="every group is fp32-issue / latency bound, not HBM bound (SURVEY.md §8d; DESIGN.md §6): traffic <= "
+                                 "algorithmic bytes, so there are no wasted re-reads to remove")
+
+        # ---- the UNMODIFIED reference operators on the same inputs, same process (oracle/ref_ops.py) ----
+        if world == 1 and not args.no_ref_gpu:
+            try:
+                ref_gpu = time_reference_gpu_ops(renderer, dev_cams[0], target_dev, kernels)
+            except Exception as ex:   # the reference build is a checker, never a dependency of the bench line
+                ref_gpu = {"unavailable": f"{type(ex).__name__}: {ex}"}
 
     if world > 1:
         dist.barrier()
@@ -376,12 +488,107 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
+        "rooflines": rooflines,
+        "ref_gpu": ref_gpu,
         "kernels_ms": kernels,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+RASTER_KERNELS = ("preprocess_fwd", "scan", "duplicate", "sort", "tile_ranges", "gather_sorted", "render_fwd", "render_bwd", "preprocess_bwd")
+TRACE_KERNELS = ("glue_quad_vertices", "bvh_build", "trace_traverse", "trace_class_lists", "trace_shade_fwd", "trace_fwd_fallback",
+                 "trace_shade_bwd", "trace_bwd_fallback")
+
+
+def time_reference_gpu_ops(renderer, cam, target, kernels_ms) -> dict:
+    """Time the reference's two operators (forward + backward, its own syncs included: that is their real cost) on exactly
+    the tensors this repository's operators see in one view: same base surfels / features / camera for the rasterizer, the
+    same reflection rays and env surfels for the tracer (GAS build included: EnvGS rebuilds it every iteration)."""
+    from envgs_b200 import glue, scene
+    from envgs_b200.rasterizer import GaussianRasterizationSettings
+    from envgs_b200.tracer import SurfelTracingSettings
+    from envgs_b200.features import sh_features
+    from oracle import ref_ops
+    from oracle import ref_trace as RT
+    dev = target.device
+    out = {}
+
+    def med(fn, warm=2, it=5):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(it):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return sorted(ts)[len(ts) // 2]
+
+    r = renderer
+    with torch.no_grad():
+        colors = sh_features(r.means, r.shs, torch.cat([r.specular, r.roughness], dim=-1), cam.campos, 3)
+        image, radii, allmap, weight, _ = r._raster(cam)
+        ref_o, ref_d = glue.reflect_rays(allmap, cam)
+    settings = GaussianRasterizationSettings(cam.H, cam.W, cam.tanfovx, cam.tanfovy, r.bg, 1.0, cam.viewmatrix, cam.projmatrix, 3, cam.campos,
+                                             False, False)
+    g_img, g_all = torch.randn_like(image) * 1e-3, torch.randn_like(allmap) * 1e-3
+    leaf = lambda t: t.detach().clone().requires_grad_(True)
+    st = {}
+
+    def rast_fwd():
+        st["leafs"] = [leaf(t) for t in (r.means, r.opacities, r.scales, r.rotations, colors)]
+        m, o, sc, ro, co = st["leafs"]
+        st["out"] = ref_ops.RefGaussianRasterizer(settings)(means3D=m, means2D=torch.zeros_like(m, requires_grad=True), opacities=o,
+                                                            colors_precomp=co, scales=sc, rotations=ro)
+
+    def rast_fwd_bwd():
+        rast_fwd()
+        torch.autograd.backward([st["out"][0], st["out"][2]], [g_img, g_all])
+
+    try:
+        f = med(rast_fwd)
+        fb = med(rast_fwd_bwd)
+        ours = sum(kernels_ms.get(k, 0.0) for k in RASTER_KERNELS)
+        out["rasterizer"] = {"ref_fwd_ms": round(f, 3), "ref_fwd_bwd_ms": round(fb, 3), "ours_fwd_bwd_kernels_ms": round(ours, 3),
+                             "speedup": round(fb / ours, 2) if ours else None,
+                             "what": "diff-surfel-rasterization-wet-ch05 (unmodified, built for sm_100a) vs this repo's kernels "
+                                     "(preprocess..render_bwd, CUDA-event device time), same surfels / features / camera"}
+    except Exception as ex:   # noqa: BLE001
+        out["rasterizer"] = {"unavailable": f"{type(ex).__name__}: {ex}"}
+
+    if r.has_env:
+        if RT.optix_available():
+            ts = SurfelTracingSettings(cam.H, cam.W, cam.tanfovx, cam.tanfovy, r.env_bg, 1.0, cam.viewmatrix, cam.projmatrix, 3, cam.campos,
+                                       False, False, 0, 0.0)
+            tracer = ref_ops.RefSurfelTracer()
+            g_rgb = torch.randn(cam.H, cam.W, 3, device=dev) * 1e-3
+
+            def trace_fwd_bwd():
+                with torch.no_grad():
+                    v, fidx = scene.quad_vertices(r.env_means, r.env_scales, r.env_rotations)     # get_disks, optix_utils.py:39-69
+                    tracer.build_acceleration_structure(v, fidx, rebuild=True)
+                lf = [leaf(t) for t in (r.env_means, r.env_opacities, r.env_scales, r.env_rotations, r.env_shs)]
+                o_, d_ = leaf(ref_o), leaf(ref_d)
+                res = tracer(o_, d_, v, lf[0], torch.zeros_like(lf[0], requires_grad=True), shs=lf[4], opacities=lf[1], scales=lf[2],
+                             rotations=lf[3], tracer_settings=ts, start_from_first=False)
+                res[0].backward(g_rgb)
+
+            fb = med(trace_fwd_bwd)
+            ours = sum(kernels_ms.get(k, 0.0) for k in TRACE_KERNELS)
+            out["tracer"] = {"ref_build_fwd_bwd_ms": round(fb, 3), "ours_build_fwd_bwd_kernels_ms": round(ours, 3),
+                             "speedup": round(fb / ours, 2) if ours else None,
+                             "what": f"diff-surfel-tracing device programs (unmodified PTX) under the driver's OptiX runtime "
+                                     f"({RT.optix_info().get('nvoptix')}) vs this repo's LBVH tracer, same reflection rays / env surfels"}
+        else:
+            out["tracer"] = {"unavailable": str(RT.optix_info().get("err"))}
+    if "speedup" in out.get("rasterizer", {}) and "speedup" in out.get("tracer", {}):
+        ref_total = out["rasterizer"]["ref_fwd_bwd_ms"] + out["tracer"]["ref_build_fwd_bwd_ms"]
+        our_total = out["rasterizer"]["ours_fwd_bwd_kernels_ms"] + out["tracer"]["ours_build_fwd_bwd_kernels_ms"]
+        out["operators_total"] = {"ref_ms": round(ref_total, 3), "ours_ms": round(our_total, 3), "speedup": round(ref_total / our_total, 2)}
+    return out
 
 
 def renderer_last_num_rendered(renderer, cam) -> int:

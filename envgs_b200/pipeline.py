@@ -67,8 +67,12 @@ class EnvGSRenderer(nn.Module):
     """Holds the base and environment surfel sets as parameters and renders / differentiates one view."""
 
     def __init__(self, base: scene.SurfelSet, env: scene.SurfelSet | None, device="cuda", fused_features: bool = True,
-                 fused_glue: bool = True):
+                 fused_glue: bool = True, rasterizer_cls=None, tracer=None):
+        """`rasterizer_cls` / `tracer`: operator objects with the reference's Python surface (GaussianRasterizer class for 5
+        channels, SurfelTracer instance).  Default: this package's.  bench.py's reference arm passes the wrappers of the
+        reference build (oracle/ref_ops.py) together with fused_* = False, i.e. the reference's own PyTorch glue."""
         super().__init__()
+        self._rasterizer_cls = rasterizer_cls if rasterizer_cls is not None else _Rasterizer5
         self.fused_features = fused_features   # False: evaluate the base SH colours in PyTorch exactly like the reference
         self.fused_glue = fused_glue           # False: per-pixel glue (reflection, dpt2norm, blend, loss) in PyTorch like the reference
         self.lambda_normal = 0.04
@@ -80,7 +84,7 @@ class EnvGSRenderer(nn.Module):
         if self.has_env:
             self.env_means, self.env_scales, self.env_rotations = P(env.means), P(env.scales), P(env.rotations)
             self.env_opacities, self.env_shs = P(env.opacities), P(env.shs)
-            self.tracer = SurfelTracer()
+            self.tracer = tracer if tracer is not None else SurfelTracer()
         self.register_buffer("bg", torch.zeros(3, device=dev))
         self.register_buffer("env_bg", torch.zeros(3, device=dev))
 
@@ -95,7 +99,7 @@ class EnvGSRenderer(nn.Module):
             rgb = torch.clamp_min(eval_sh_deg3(self.shs, dirs) + 0.5, 0.0)
             colors = torch.cat([rgb, self.specular, self.roughness], dim=-1)
         means2D = torch.zeros_like(self.means, requires_grad=True)
-        image, radii, allmap, weight = _Rasterizer5(settings)(means3D=self.means, means2D=means2D, opacities=self.opacities,
+        image, radii, allmap, weight = self._rasterizer_cls(settings)(means3D=self.means, means2D=means2D, opacities=self.opacities,
                                                               colors_precomp=colors, scales=self.scales, rotations=self.rotations)
         return image, radii, allmap, weight, means2D
 
