@@ -70,6 +70,19 @@ class TraceGrads(C.Structure):
     ]
 
 
+class DensifyParams(C.Structure):
+    _fields_ = [("P", C.c_int32), ("n_split", C.c_int32), ("split_ratio", C.c_float), ("grad_threshold", C.c_float),
+                ("size_threshold", C.c_float), ("split_screen_threshold", C.c_float), ("min_opacity", C.c_float),
+                ("min_gradient", C.c_float)]
+
+
+class RowArray(C.Structure):
+    _fields_ = [("src", _fp), ("dst", _fp), ("width", C.c_int32), ("role", C.c_int32)]
+
+
+ROW_PLAIN, ROW_XYZ, ROW_SCALING, ROW_OPT_STATE, ROW_STAT_GRAD, ROW_STAT_DENOM, ROW_STAT_RADII, ROW_STAT_WEIGHT = 0, 1, 2, 4, 5, 6, 7, 8
+
+
 # every symbol include/envgs_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
     "envgs_last_error", "envgs_version", "envgs_raster_forward", "envgs_raster_backward", "envgs_mark_visible",
@@ -78,6 +91,7 @@ EXPORTS = [
     "envgs_trace_backward", "envgs_launch_count", "envgs_profile_enable", "envgs_profile_report", "envgs_debug_trace_stats", "envgs_trace_cache_bytes", "envgs_sh_features_forward", "envgs_sh_features_backward",
     "envgs_glue_reflect_forward", "envgs_glue_reflect_backward", "envgs_glue_blend_loss_forward", "envgs_glue_blend_loss_backward",
     "envgs_adam_step", "envgs_glue_quad_vertices",
+    "envgs_densify_stats", "envgs_densify_plan_scratch_bytes", "envgs_densify_plan", "envgs_densify_apply", "envgs_rows_gather",
 ]
 
 _lib = None
@@ -142,6 +156,17 @@ def lib() -> C.CDLL:
     L.envgs_adam_step.argtypes = [C.c_uint64] + [C.c_void_p] * 4 + [C.c_int32] + [C.c_float] * 5 + [C.c_int32, C.c_void_p]
     L.envgs_debug_trace_stats.restype = C.c_int
     L.envgs_debug_trace_stats.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_uint64)]
+    L.envgs_densify_stats.restype = C.c_int
+    L.envgs_densify_stats.argtypes = [C.c_int32] + [C.c_void_p] * 8
+    L.envgs_densify_plan_scratch_bytes.restype = C.c_size_t
+    L.envgs_densify_plan_scratch_bytes.argtypes = [C.c_int32]
+    L.envgs_densify_plan.restype = C.c_int
+    L.envgs_densify_plan.argtypes = [C.POINTER(DensifyParams)] + [C.c_void_p] * 7 + [C.POINTER(C.c_int32), C.c_void_p, C.c_size_t, C.c_void_p]
+    L.envgs_densify_apply.restype = C.c_int
+    L.envgs_densify_apply.argtypes = [C.POINTER(DensifyParams), C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.POINTER(RowArray)] + \
+        [C.c_void_p] * 6
+    L.envgs_rows_gather.restype = C.c_int
+    L.envgs_rows_gather.argtypes = [C.c_int64, C.c_void_p, C.c_int32, C.POINTER(RowArray), C.c_void_p]
     _lib = L
     return L
 

@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(HERE, "_build")
 LIB_PATH = os.path.join(HERE, "libenvgs_b200.so")
-SOURCES = ["capi.cu", "raster_forward.cu", "raster_backward.cu", "lbvh.cu", "trace.cu", "trace_fast.cu", "features.cu", "glue.cu", "optim.cu"]
+SOURCES = ["capi.cu", "raster_forward.cu", "raster_backward.cu", "lbvh.cu", "trace.cu", "trace_fast.cu", "features.cu", "glue.cu", "optim.cu", "densify.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",

@@ -113,6 +113,50 @@ size_t envgs_raster_img_bytes(int32_t width, int32_t height);
 size_t envgs_raster_binning_bytes(int32_t num_rendered);
 
 /* ------------------------------------------------------------------------------------------------ */
+/* Densification / pruning of a surfel set on the device.                     */
+/* Replaces the mask-gather / torch.cat implementation of                                            */
+/*   easyvolcap/utils/gaussian2d_utils.py:517-592 (optimizer state), :623-716 (statistics),           */
+/*   :718-760 (clone / split), :762-836 (selection rules), :867-911 (densify_and_prune, statistics).  */
+/* ------------------------------------------------------------------------------------------------ */
+typedef struct envgs_densify_params {
+    int32_t P;                    /* rows before the update */
+    int32_t n_split;              /* children per split surfel (densify_and_split: 2) */
+    float split_ratio;            /* 0.8: child scale = scale / (ratio * n_split) */
+    float grad_threshold;         /* densify_grad_threshold */
+    float size_threshold;         /* densify_size_threshold * spatial_scale */
+    float split_screen_threshold; /* < 0: disabled (None) */
+    float min_opacity;            /* < 0: disabled */
+    float min_gradient;           /* < 0: disabled */
+} envgs_densify_params;
+
+enum { ENVGS_ROW_PLAIN = 0, ENVGS_ROW_XYZ = 1, ENVGS_ROW_SCALING = 2, ENVGS_ROW_OPT_STATE = 4, ENVGS_ROW_STAT_GRAD = 5,
+       ENVGS_ROW_STAT_DENOM = 6, ENVGS_ROW_STAT_RADII = 7, ENVGS_ROW_STAT_WEIGHT = 8 };
+typedef struct envgs_row_array {  /* one (rows, width) fp32 array that follows the surfel rows */
+    const float* src;
+    float* dst;
+    int32_t width;
+    int32_t role;                 /* ENVGS_ROW_*: how new rows (clones, split children) are derived from the source row */
+} envgs_row_array;
+
+/* add_densification_stats (:901-911) + max_radii2D update (envgs_sampler.py:250-253) for rows with radii > 0 */
+int envgs_densify_stats(int32_t P, const float* viewspace_grad, const int32_t* radii, const float* weight, float* grad_accum,
+                        float* denom, float* weight_accum, float* max_radii2D, void* stream);
+size_t envgs_densify_plan_scratch_bytes(int32_t P);
+/* clone -> split -> prune_min_opacity_and_gradients resolved per source row; plan = 4*P int32, counts = {kept originals, kept
+ * clones, split originals, split clones}; new row count = counts[0] + counts[1] + n_split * (counts[2] + counts[3]).
+ * Synchronises `stream` (the caller allocates the new buffers from counts_host). */
+int envgs_densify_plan(const envgs_densify_params* p, const float* scaling_act, const float* opacity_act, const float* grad_accum,
+                       const float* denom, const float* max_radii2D, int32_t* plan, int32_t* counts_dev, int32_t counts_host[4],
+                       void* scratch, size_t scratch_bytes, void* stream);
+/* scatter every array's rows to their planned destinations (noise: (n_split, 2, P, 2) standard normals; weight_max: device
+ * {max weight over the originals, max over originals and clones} or NULL) */
+int envgs_densify_apply(const envgs_densify_params* p, const int32_t* plan, const int32_t counts[4], int32_t n_arrays,
+                        const envgs_row_array* arrays, const float* xyz, const float* scaling_act, const float* rotation,
+                        const float* noise, const float* weight_max, void* stream);
+/* dst[a][j,:] = src[a][index[j],:] for all arrays (prune_points + _prune_optimizer + prune_stats for an index list) */
+int envgs_rows_gather(int64_t M, const int64_t* index, int32_t n_arrays, const envgs_row_array* arrays, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ */
 /* Tracer                                                                                             */
 /* ------------------------------------------------------------------------------------------------ */
 
