@@ -94,60 +94,71 @@ def test_shard_views_round_robin():
 
 
 class _ToyRenderer(torch.nn.Module):
-    """CPU stand-in with the renderer's interface (forward(cam) -> dict, loss(out, target))."""
+    """CPU stand-in with the renderer's interface (forward(cam) -> dict, loss(out, target)); `env_c` plays the environment
+    set: created last, so its gradient is produced FIRST in the backward pass and its exchange is launched from the hook."""
 
     def __init__(self):
         super().__init__()
         g = torch.Generator().manual_seed(0)
         self.a = torch.nn.Parameter(torch.randn(7, 3, generator=g))
         self.b = torch.nn.Parameter(torch.randn(5, generator=g))
+        self.env_c = torch.nn.Parameter(torch.randn(4, 2, generator=g))
 
     def forward(self, cam, target=None):
-        return {"rgb": (self.a * cam).sum() + (self.b ** 2).sum() * cam.mean()}
+        base = (self.a * cam).sum() + (self.b ** 2).sum() * cam.mean()
+        return {"rgb": base * (1.0 + 0.1 * (self.env_c ** 3).sum() * cam.mean())}
 
     def loss(self, out, target):
         return (out["rgb"] - target) ** 2
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, overlap):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
     from envgs_b200.dist import ViewParallelTrainer, init_process_group_from_env
     init_process_group_from_env("gloo")
     r = _ToyRenderer()
-    tr = ViewParallelTrainer(r, average=False, optimizer=False)
+    tr = ViewParallelTrainer(r, average=False, optimizer=False, overlap=overlap)
     cam = torch.full((7, 3), float(rank + 1))
     tr.step(cam, torch.tensor(0.5))
-    q.put((rank, tr.flat.flat_grad.clone(), r.a.grad.data_ptr() == tr.flat.flat_grad.data_ptr()))
+    views = all(tr.flat.grad_is_view(k) for k in range(3))
+    q.put((rank, {n: p.grad.tolist() for n, p in r.named_parameters()}, views, tr._early_work is not None, tr.flat.names,
+           (tr.flat.late_range, tr.flat.early_range)))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_view_parallel_gradient_allreduce_gloo_world2():
+@pytest.mark.parametrize("overlap", [True, False])
+def test_view_parallel_gradient_allreduce_gloo_world2(overlap):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + os.getpid() % 300
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29600 + (os.getpid() + int(overlap)) % 300
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, overlap)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=120) for _ in range(2)], key=lambda t: t[0])
     for p in procs:
         p.join(timeout=60)
     # expected: sum over the two ranks of the single-process gradients
-    expect = torch.zeros(7 * 3 + 5)
+    expect = None
     for rank in range(2):
         r = _ToyRenderer()
         cam = torch.full((7, 3), float(rank + 1))
         r.loss(r(cam), torch.tensor(0.5)).backward()
-        expect += torch.cat([r.a.grad.reshape(-1), r.b.grad.reshape(-1)])
-    for rank, flat_grad, is_view in res:
+        g = {n: p.grad.clone() for n, p in r.named_parameters()}
+        expect = g if expect is None else {n: expect[n] + g[n] for n in g}
+    for rank, grads, is_view, early_launched, names, (late, early) in res:
         assert is_view                                        # parameter grads are views into the single flat buffer
-        assert torch.allclose(flat_grad, expect, rtol=1e-5, atol=1e-5)
+        assert names == ["a", "b", "env_c"] and late[0] == 0 and early[0] == late[1] and late[1] % 8192 == 0
+        assert early_launched == overlap                      # the environment group's exchange started from the gradient hook
+        for n in expect:
+            assert torch.allclose(torch.tensor(grads[n]), expect[n], rtol=1e-5, atol=1e-5), n
 
 
 def test_bench_reference_arm_contract():
-    """`bench.py --impl reference` (the CPU oracle arm) prints one JSON line with the keys the driver reads and never touches CUDA."""
+    """`bench.py --impl reference` without a GPU (the CPU oracle port) prints one JSON line with the keys the driver reads and never
+    touches CUDA."""
     import json, subprocess, sys
     env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "tiny", "--steps", "1",
