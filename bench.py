@@ -26,9 +26,11 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
+TRACE_DEPTH = {"config5": 1}      # trace segments beyond the first (BASELINE config 5: 2-bounce)
 WORKLOADS = {
     # name: (P_base, P_env, H, W)
     "config3": (1_000_000, 262_144, 1080, 1920),
+    "config5": (4_000_000, 1_048_576, 2160, 3840),
     "config2": (500_000, 0, 1080, 1920),
     "config1": (10_000, 0, 256, 256),
     "tiny": (20_000, 8_192, 270, 480),
@@ -306,7 +308,9 @@ def main():
 
     base = scene.make_base_set(Pb, seed=0, s0=s0)
     env = scene.make_env_set(Pe, seed=1, s0=s0) if Pe > 0 else None
-    renderer = EnvGSRenderer(base, env, device=dev)
+    if TRACE_DEPTH.get(args.workload, 0) and env is not None:
+        env.specular.fill_(0.5)                           # every second-segment ray continues unless its first segment saw nothing
+    renderer = EnvGSRenderer(base, env, device=dev, max_trace_depth=TRACE_DEPTH.get(args.workload, 0))
     trainer = ViewParallelTrainer(renderer, lr=1e-6, average=True, optimizer=True, overlap=not args.no_overlap,
                                   shard_optimizer=not args.no_shard)
     n_views = 138                                         # sedan-sized view list
@@ -512,7 +516,7 @@ def main():
         "metric": "render Mpix/s (fwd+bwd, rasterize+trace)", "value": round(value, 3), "unit": "Mpix/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {Pb} base + {Pe} env surfels, SH deg 3, {W}x{H}, 1-bounce reflection trace, "
+        "config": {"workload": f"{args.workload}: {Pb} base + {Pe} env surfels, SH deg 3, {W}x{H}, {1 + TRACE_DEPTH.get(args.workload, 0)}-segment reflection trace, "
                                f"fwd+bwd + BVH rebuild + grad all-reduce + fused Adam, 1 view/rank/step",
                    "l2": "inputs_larger_than_L2 (surfel parameters 240+61 MB, maps 25-265 MB each vs 126 MB L2)",
                    "parallelism": f"view-parallel x{world}"},

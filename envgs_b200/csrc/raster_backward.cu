@@ -168,12 +168,14 @@ __global__ void __launch_bounds__(256, RBWD_MINBLOCKS) render_bwd_kernel(
                 float3 k = pxf * Tw - Tu;
                 float3 l = pyf * Tw - Tv;
                 float3 p = cross(k, l);
-                if (p.z != 0.0f) {
+                float dx = r2.y - pxf, dy = r2.z - pyf;
+                float rho2d = FILTER_INV_SQUARE * (dx * dx + dy * dy);
+                const float tau = st.r3[sj].w;                   // the forward kernel's early reject, same expression, same bits
+                const bool reject = (p.x * p.x + p.y * p.y > tau * (p.z * p.z)) && (rho2d > tau);
+                if (!reject && p.z != 0.0f) {
                     const float rz = px_rcp(p.z);                // same reciprocal form as the forward kernel
                     float sx = px_div(p.x, p.z, rz), sy = px_div(p.y, p.z, rz);
                     float rho3d = sx * sx + sy * sy;
-                    float dx = r2.y - pxf, dy = r2.z - pyf;
-                    float rho2d = FILTER_INV_SQUARE * (dx * dx + dy * dy);
                     float rho = fminf(rho3d, rho2d);
                     float c_d = (rho3d <= rho2d) ? (sx * Tw.x + sy * Tw.y) + Tw.z : Tw.z;
                     float power = -0.5f * rho;

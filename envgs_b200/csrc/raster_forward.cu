@@ -241,7 +241,10 @@ __global__ void __launch_bounds__(256) preprocess_kernel(
     g.rec[4 * (size_t)idx + 0] = make_float4(Tu.x, Tu.y, Tu.z, Tv.x);
     g.rec[4 * (size_t)idx + 1] = make_float4(Tv.y, Tv.z, Tw.x, Tw.y);
     g.rec[4 * (size_t)idx + 2] = make_float4(Tw.z, center.x, center.y, opacity);
-    g.rec[4 * (size_t)idx + 3] = make_float4(normal.x, normal.y, normal.z, p_view.z);
+    // .w: conservative threshold of the tile kernels' early reject.  A pair contributes iff min(rho3d, rho2d) <= 2 ln(255 o);
+    // the margin (0.2 % + 4e-3) is three orders above the fp32 noise of either side's evaluation, so the reject only ever drops
+    // pairs the exact test `alpha < 1/255` drops (forward.cu:380-382) and every borderline pair still takes the exact path.
+    g.rec[4 * (size_t)idx + 3] = make_float4(normal.x, normal.y, normal.z, 2.0f * logf(255.0f * opacity) * 1.002f + 4e-3f);
 
     // exact culling: intersect the reference rect with the tiles the contributing region can touch
     float bx0, by0, bx1, by1;
@@ -416,12 +419,17 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(
                 float3 k = pxf * Tw - Tu;
                 float3 l = pyf * Tw - Tv;
                 float3 p = cross(k, l);
-                if (p.z != 0.0f) {
-                    const float rz = px_rcp(p.z);                // one reciprocal instead of two divisions (<= 1 ulp apart)
+                float dx = r2.y - pxf, dy = r2.z - pyf;
+                float rho2d = FILTER_INV_SQUARE * (dx * dx + dy * dy);
+                // Early reject without the two divisions and the exponential: rho3d = (p.x^2 + p.y^2) / p.z^2 > tau and
+                // rho2d > tau  =>  alpha < 1/255.  ~80 % of the (pixel, surfel) pairs that survive the warp's box test end here.
+                // (NaNs compare false and fall through to the exact path.)
+                const float tau = st.r3[sj].w;
+                const bool reject = (p.x * p.x + p.y * p.y > tau * (p.z * p.z)) && (rho2d > tau);
+                if (!reject && p.z != 0.0f) {
+                    const float rz = px_rcp(p.z);                // fast-math build: one reciprocal instead of two divisions
                     float sx = px_div(p.x, p.z, rz), sy = px_div(p.y, p.z, rz);
                     float rho3d = sx * sx + sy * sy;
-                    float dx = r2.y - pxf, dy = r2.z - pyf;
-                    float rho2d = FILTER_INV_SQUARE * (dx * dx + dy * dy);
                     float rho = fminf(rho3d, rho2d);
                     float depth = (rho3d <= rho2d) ? (sx * Tw.x + sy * Tw.y) + Tw.z : Tw.z;
                     float power = -0.5f * rho;

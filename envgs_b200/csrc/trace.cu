@@ -598,16 +598,21 @@ __global__ void __launch_bounds__(TR_THREADS) trace_kernel(const TraceParams p) 
 
 int launch_trace(bool bwd, Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_out* o,
                  const envgs_trace_grads* g, const int* ray_list, const unsigned int* ray_count, cudaStream_t stream) {
-    static int sm_count = 0, occ_f = 0, occ_b = 0;
-    if (sm_count == 0) {
-        int dev = 0;
-        ENVGS_CUDA_TRY(cudaGetDevice(&dev));
-        ENVGS_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-        ENVGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, trace_kernel<false>, TR_THREADS, 0));
-        ENVGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, trace_kernel<true>, TR_THREADS, 0));
-        if (occ_f < 1) occ_f = 1;
-        if (occ_b < 1) occ_b = 1;
+    // launch geometry is a property of the CURRENT device: cached per device id, not once per process
+    static int sm_counts[64] = {0}, occ_fs[64] = {0}, occ_bs[64] = {0};
+    int dev = 0;
+    ENVGS_CUDA_TRY(cudaGetDevice(&dev));
+    const int slot = dev & 63;
+    if (sm_counts[slot] == 0) {
+        int n = 0, f = 0, b = 0;
+        ENVGS_CUDA_TRY(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+        ENVGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&f, trace_kernel<false>, TR_THREADS, 0));
+        ENVGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, trace_kernel<true>, TR_THREADS, 0));
+        occ_fs[slot] = f < 1 ? 1 : f;
+        occ_bs[slot] = b < 1 ? 1 : b;
+        sm_counts[slot] = n;
     }
+    const int sm_count = sm_counts[slot], occ_f = occ_fs[slot], occ_b = occ_bs[slot];
     TraceParams p;
     p.nodes = bvh.nodes; p.prims = bvh.prims; p.a = a;
     if (o) p.o = *o; else memset(&p.o, 0, sizeof(p.o));

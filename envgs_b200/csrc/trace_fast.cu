@@ -999,14 +999,18 @@ struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; };
 
 int trace_forward_fast(Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_out& o,
                        void* cache, cudaStream_t stream, const SideStream& side) {
-    static int sm_count = 0, occ = 0;
-    if (sm_count == 0) {
-        int dev = 0;
-        ENVGS_CUDA_TRY(cudaGetDevice(&dev));
-        ENVGS_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-        ENVGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, traverse_kernel<false>, TF_THREADS, 0));
-        if (occ < 1) occ = 1;
+    static int sm_counts[64] = {0}, occs[64] = {0};   // per device id (the handle may live on any GPU of the process)
+    int dev = 0;
+    ENVGS_CUDA_TRY(cudaGetDevice(&dev));
+    const int slot = dev & 63;
+    if (sm_counts[slot] == 0) {
+        int n = 0, oc = 0;
+        ENVGS_CUDA_TRY(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+        ENVGS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc, traverse_kernel<false>, TF_THREADS, 0));
+        occs[slot] = oc < 1 ? 1 : oc;
+        sm_counts[slot] = n;
     }
+    const int sm_count = sm_counts[slot], occ = occs[slot];
     FastParams p;
     memset(&p, 0, sizeof(p));
     p.nodes = bvh.nodes; p.nodes4 = bvh.nodes4; p.prims = bvh.prims; p.a = a; p.o = o;

@@ -67,12 +67,25 @@ class EnvGSRenderer(nn.Module):
     """Holds the base and environment surfel sets as parameters and renders / differentiates one view."""
 
     def __init__(self, base: scene.SurfelSet, env: scene.SurfelSet | None, device="cuda", fused_features: bool = True,
-                 fused_glue: bool = True, rasterizer_cls=None, tracer=None):
+                 fused_glue: bool = True, rasterizer_cls=None, tracer=None, max_trace_depth: int = 0, specular_threshold: float = 0.01,
+                 ray_filter: str | None = None, specular_filtering_percent: float = 0.75):
         """`rasterizer_cls` / `tracer`: operator objects with the reference's Python surface (GaussianRasterizer class for 5
         channels, SurfelTracer instance).  Default: this package's.  bench.py's reference arm passes the wrappers of the
         reference build (oracle/ref_ops.py) together with fused_* = False, i.e. the reference's own PyTorch glue."""
         super().__init__()
         self._rasterizer_cls = rasterizer_cls if rasterizer_cls is not None else _Rasterizer5
+        # max_trace_depth = 1: the traced set carries its own specular / roughness (`others_precomp`) and a ray continues along
+        # the reflection about the accumulated normal while the accumulated specular exceeds the threshold (BASELINE config 5;
+        # TRACE/optix_tracer/forward.cu:453-559).  EnvGS' own configuration traces a single segment (0).
+        self.max_trace_depth, self.specular_threshold = int(max_trace_depth), float(specular_threshold)
+        # Which pixels send a reflection ray (envgs_sampler.py:433-447): None = all (the reference's default configuration),
+        # "acc" = accumulated alpha > 0.75, "specular" = rendered specular above its `specular_filtering_percent` quantile — the
+        # reference's two optional filters, traced as a compact (1, S) ray list exactly like there — and "nonempty" = pixels with
+        # alpha > 0: a pixel no base surfel reaches has specular == 0 exactly, so its environment colour is multiplied by zero
+        # and no parameter gradient can depend on it; image, loss and every parameter gradient are unchanged, only the traced
+        # set's blend-weight statistics (`wet`) lose those rays' contributions.
+        assert ray_filter in (None, "acc", "specular", "nonempty")
+        self.ray_filter, self.specular_filtering_percent = ray_filter, specular_filtering_percent
         self.fused_features = fused_features   # False: evaluate the base SH colours in PyTorch exactly like the reference
         self.fused_glue = fused_glue           # False: per-pixel glue (reflection, dpt2norm, blend, loss) in PyTorch like the reference
         self.lambda_normal = 0.04
@@ -84,6 +97,8 @@ class EnvGSRenderer(nn.Module):
         if self.has_env:
             self.env_means, self.env_scales, self.env_rotations = P(env.means), P(env.scales), P(env.rotations)
             self.env_opacities, self.env_shs = P(env.opacities), P(env.shs)
+            if self.max_trace_depth > 0:
+                self.env_specular, self.env_roughness = P(env.specular), P(env.roughness)
             self.tracer = tracer if tracer is not None else SurfelTracer()
         self.register_buffer("bg", torch.zeros(3, device=dev))
         self.register_buffer("env_bg", torch.zeros(3, device=dev))
@@ -125,16 +140,28 @@ class EnvGSRenderer(nn.Module):
                 v, f = scene.quad_vertices(self.env_means, self.env_scales, self.env_rotations)
             self.tracer.build_acceleration_structure(v, f, rebuild=True)   # every training iteration (optix_utils.py:71-85)
         s = SurfelTracingSettings(cam.H, cam.W, cam.tanfovx, cam.tanfovy, self.env_bg, 1.0, cam.viewmatrix, cam.projmatrix, 3,
-                                  cam.campos, False, False, 0, 0.0)
+                                  cam.campos, False, False, self.max_trace_depth, self.specular_threshold if self.max_trace_depth else 0.0)
         grads3D = torch.zeros_like(self.env_means, requires_grad=True)
+        others = torch.cat([self.env_specular, self.env_roughness], dim=-1) if self.max_trace_depth > 0 else None
         rgb, dpt, acc, norm, dist, aux, mid, wet = self.tracer(ref_o, ref_d, v, self.env_means, grads3D, shs=self.env_shs,
+                                                               others_precomp=others,
                                                                opacities=self.env_opacities, scales=self.env_scales,
                                                                rotations=self.env_rotations, tracer_settings=s,
                                                                start_from_first=False)
         return dict(rgb=rgb, dpt=dpt, acc=acc, norm=norm, wet=wet, grads3D=grads3D)
 
+    def _ray_mask(self, out: dict) -> torch.Tensor | None:
+        if self.ray_filter is None:
+            return None
+        if self.ray_filter == "specular":
+            spec = out["specular"][0]
+            return spec > torch.quantile(spec.reshape(-1)[:: max(1, spec.numel() // 4_000_000)], self.specular_filtering_percent)
+        if self.ray_filter == "acc":
+            return out["alpha"][0] > 0.75
+        return out["alpha"][0] > 0.0
+
     def forward(self, cam: scene.Camera, target: torch.Tensor | None = None) -> dict:
-        if self.fused_glue and target is not None:
+        if self.fused_glue and target is not None and self.ray_filter is None:
             return self._forward_fused(cam, target)
         out = self.rasterize_base(cam)
         rgb = out["render"].permute(1, 2, 0)                     # (H,W,3)
@@ -144,9 +171,17 @@ class EnvGSRenderer(nn.Module):
             n = norm_map / (norm_map.norm(dim=-1, keepdim=True) + 1e-8)
             ref_d = ray_d - 2 * (ray_d * n).sum(-1, keepdim=True) * n
             ref_o = ray_o + ray_d * out["depth"].permute(1, 2, 0)
-            env = self.trace_env(cam, ref_o.contiguous(), ref_d.contiguous())
             spec = out["specular"].permute(1, 2, 0)
-            rgb = (1 - spec) * rgb + spec * env["rgb"]          # envgs_sampler.py:474
+            msk = self._ray_mask(out)
+            if msk is None:
+                env = self.trace_env(cam, ref_o.contiguous(), ref_d.contiguous())
+                rgb = (1 - spec) * rgb + spec * env["rgb"]      # envgs_sampler.py:474
+            else:                                               # compact ray list (1, S, 3), envgs_sampler.py:438-447, :466-470
+                env = self.trace_env(cam, ref_o[msk][None].contiguous(), ref_d[msk][None].contiguous())
+                blended = rgb.clone()
+                blended[msk] = (1 - spec[msk]) * rgb[msk] + spec[msk] * env["rgb"][0]
+                rgb = blended
+                out["ref_msk"] = msk
             out["env"] = env
         out["rgb"] = rgb
         return out

@@ -42,14 +42,22 @@ def _f32c(t: torch.Tensor | None, device) -> torch.Tensor | None:
 
 
 _ALLOC_QUANTUM = 32 << 20
-_ALLOC_HWM: dict = {}   # (device, buffer role) -> largest rounded request so far
+_ALLOC_HWM: dict = {}   # (device, H, W, C) -> largest rounded `binning` request so far
+
+
+def reset_scratch_high_water_marks() -> None:
+    """Forget the binning-buffer high-water marks (call after densify / prune shrank the set, or when switching to a much
+    smaller resolution); the next frames re-learn them."""
+    _ALLOC_HWM.clear()
+
 
 
 class _Scratch:
     """Allocator callbacks handed to the C ABI: three torch byte tensors owned by the autograd context."""
 
-    def __init__(self, device):
+    def __init__(self, device, shape_key=None):
         self.device = device
+        self.shape_key = shape_key
         self.bufs = {}
         self.cbs = {}
         for name in ("geom", "binning", "img"):
@@ -62,10 +70,12 @@ class _Scratch:
             # (measured: reserved memory creeping from 3 to 10 GB and a 30-110 ms cudaMalloc stall every few views).  Sizes
             # are therefore rounded up to a coarse quantum and never shrink below the largest request seen on this device:
             # after the first few views every step issues the identical allocation sequence and the allocator is quiet.
+            # Only `binning` varies; `geom` and `img` are fixed for a given (P, H, W) and are allocated at their exact size, so a
+            # large frame does not inflate the scratch of later low-resolution / other-channel calls.
             n = max(int(nbytes), 1)
-            if n > (4 << 20):
+            if name == "binning" and n > (4 << 20):
                 n = (n + _ALLOC_QUANTUM - 1) // _ALLOC_QUANTUM * _ALLOC_QUANTUM
-                key = (str(self.device), name)
+                key = (str(self.device), self.shape_key)
                 n = max(n, _ALLOC_HWM.get(key, 0))
                 _ALLOC_HWM[key] = n
             try:
@@ -156,7 +166,7 @@ def make_module(C_channels: int):
             others = alloc((7, H, W), dtype=torch.float32, device=device)
             weight = torch.zeros((P, 1), dtype=torch.float32, device=device)
             radii = alloc((P,), dtype=torch.int32, device=device)
-            scratch = _Scratch(device)
+            scratch = _Scratch(device, (H, W, C_channels))
 
             args = _make_args(C_channels, s, bg, m3, shc, col, opa, sc, rot, cov, vm, pm, cam)
             out = _lib.RasterOut(_lib.ptr(color), _lib.ptr(others), _lib.ptr(weight), _lib.ptr(radii))

@@ -46,13 +46,39 @@ class _Context:
 
     def __init__(self):
         self._lib = _lib.lib()
-        self.handle = self._lib.envgs_tracer_create()
-        if not self.handle:
-            raise RuntimeError("envgs_tracer_create failed: " + self._lib.envgs_last_error().decode())
+        self._handle = None          # created lazily, under the device guard of the tensors it will serve
         self.storage = None
         self.num_surfels = 0
         self._cb = _lib.ALLOC_FN(self._alloc)
         self._device = None
+
+    @property
+    def handle(self):
+        if self._handle is None:
+            raise RuntimeError("the acceleration structure has not been built: call build_acceleration_structure first")
+        return self._handle
+
+    def _ensure(self, device: torch.device):
+        """The native handle owns a work counter, a side stream and two events: they belong to ONE CUDA device, so it is
+        created under `torch.cuda.device(device)` and re-created if the module is later used on another device."""
+        if self._handle is not None and self._device == device:
+            return
+        self._destroy()
+        with torch.cuda.device(device):
+            self._handle = self._lib.envgs_tracer_create()
+        if not self._handle:
+            raise RuntimeError("envgs_tracer_create failed: " + self._lib.envgs_last_error().decode())
+        self._device = device
+        self.storage, self.num_surfels = None, 0
+
+    def _destroy(self):
+        if self._handle:
+            if self._device is not None:
+                with torch.cuda.device(self._device):
+                    self._lib.envgs_tracer_destroy(self._handle)
+            else:
+                self._lib.envgs_tracer_destroy(self._handle)
+            self._handle = None
 
     def _alloc(self, _user, nbytes):
         try:
@@ -67,7 +93,10 @@ class _Context:
         if not vertices.is_cuda:
             raise RuntimeError("vertices must be a CUDA tensor")
         v = vertices.detach().to(torch.float32).contiguous()
-        self._device = v.device
+        self._ensure(v.device)
+        if v.shape[0] == 0:          # a set pruned to zero surfels: nothing to build, forward returns the background
+            self.num_surfels = 0
+            return
         with torch.cuda.device(v.device):
             _lib.check(self._lib.envgs_tracer_build(self.handle, _lib.ptr(v), v.shape[0], int(rebuild), self._cb, None,
                                                     torch.cuda.current_stream(v.device).cuda_stream),
@@ -76,9 +105,7 @@ class _Context:
 
     def __del__(self):
         try:
-            if self.handle:
-                self._lib.envgs_tracer_destroy(self.handle)
-                self.handle = None
+            self._destroy()
         except Exception:
             pass
 
@@ -125,6 +152,21 @@ class _TraceSurfels(torch.autograd.Function):
         device = means3D.device
         P = means3D.shape[0]
         H, W = ray_o.shape[0], ray_o.shape[1]
+        if optix_context._device is not None and optix_context._device != device:
+            raise RuntimeError(f"the acceleration structure was built on {optix_context._device} but the surfels are on {device}")
+        if P == 0:
+            # an empty traced set (e.g. pruned to zero surfels): every ray sees the background; no gradient flows anywhere
+            f = dict(dtype=torch.float32, device=device)
+            bg = s.bg.detach().to(**f).reshape(-1)[:3]
+            rgb = bg.expand(H, W, 3).contiguous()
+            mid = torch.zeros((H, W, MID_CHANNELS * (MAX_TRACE_DEPTH + 1)), **f)
+            mid[..., 0:3], mid[..., 3:6], mid[..., 13:16] = ray_o.detach(), ray_d.detach(), rgb
+            ctx.empty = True
+            wet = torch.zeros((0, 1), **f)
+            ctx.mark_non_differentiable(mid, wet)
+            return (rgb, torch.zeros((H, W, 1), **f), torch.zeros((H, W, 1), **f), torch.zeros((H, W, 3), **f), torch.zeros((H, W, 1), **f),
+                    torch.zeros((H, W, AUX_CHANNELS), **f), mid, wet)
+        ctx.empty = False
 
         ro, rd = _f32c(ray_o, device), _f32c(ray_d, device)
         m3, sh, col, oth = _f32c(means3D, device), _f32c(shs, device), _f32c(colors_precomp, device), _f32c(others_precomp, device)
@@ -182,6 +224,8 @@ class _TraceSurfels(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out_rgb, grad_out_dpt, grad_out_acc, grad_out_norm, grad_out_dist, grad_out_aux, grad_mid_val,
                  grad_acc_wet):
+        if ctx.empty:               # nothing was traced: every input's gradient is zero (None)
+            return (None,) * 16
         L = _lib.lib()
         s = ctx.tracer_settings
         ro, rd, m3, sh, col, oth, opa, sc, rot, out_rgb, out_dpt, out_acc, out_norm, out_dist, out_aux, mid_val = ctx.saved_tensors

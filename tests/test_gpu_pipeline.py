@@ -121,3 +121,34 @@ def test_fused_quad_vertices_match_pytorch(built_lib):
     v, f = glue.quad_vertices(env.means, env.scales, rots)
     assert torch.equal(f, f_ref)
     assert float((v - v_ref).abs().max()) <= 2e-6 * float(v_ref.abs().max())
+
+
+def test_nonempty_ray_filter_changes_no_parameter_gradient(built_lib):
+    """Pixels no base surfel reaches have specular == 0 exactly: skipping their reflection rays (ray_filter="nonempty", the
+    exact counterpart of the reference's optional acc / specular filters, envgs_sampler.py:433-447) must leave the image, the
+    loss and every parameter gradient unchanged."""
+    import torch
+    from envgs_b200 import scene
+    from envgs_b200.pipeline import EnvGSRenderer
+    dev = torch.device("cuda")
+    base, env = scene.make_base_set(6000, seed=0, s0=0.03), scene.make_env_set(4000, seed=1, s0=0.04)
+    base.means.mul_(0.5)                                        # leave an empty border around the object
+    cam = scene.ring_cameras(1, 96, 128, seed=2)[0].to(dev)
+    target = torch.rand(96, 128, 3, generator=torch.Generator().manual_seed(3)).to(dev)
+    res = {}
+    for flt in (None, "nonempty", "acc"):
+        r = EnvGSRenderer(base, env, device=dev, fused_glue=False, ray_filter=flt)
+        out = r(cam)
+        loss = r.loss(out, target)
+        loss.backward()
+        res[flt] = (out, float(loss), {n: p.grad.clone() for n, p in r.named_parameters()})
+    full, skip = res[None], res["nonempty"]
+    msk = skip[0]["ref_msk"]
+    assert 0.05 < float((~msk).float().mean()) < 0.9            # the case really skips rays
+    assert torch.equal(full[0]["rgb"], skip[0]["rgb"]) or float((full[0]["rgb"] - skip[0]["rgb"]).abs().max()) < 1e-7
+    assert abs(full[1] - skip[1]) <= 1e-7 * abs(full[1])
+    for n in full[2]:
+        a, b = full[2][n], skip[2][n]
+        assert float((a - b).norm()) <= 1e-5 * float(a.norm()) + 1e-12, n
+    # the reference's acc filter traces fewer rays still and only needs to run
+    assert int(res["acc"][0]["ref_msk"].sum()) <= int(msk.sum())

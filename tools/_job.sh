@@ -1,3 +1,7 @@
-for f in "" "--no-overlap" "--no-shard" "--no-overlap --no-shard"; do
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 bench.py --gpus 2 --steps 30 --warmup 5 --no-profile $f 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$f', d['ms_per_step'], d['e2e']['ms_per_step'])"
-done
+python -m pytest tests -m gpu -q --tb=short -x 2>&1 | tail -12
+python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-ref-gpu > gpurun_out/bench_r2_v3.json 2> gpurun_out/bench_r2_v3.err; python - <<'PY'
+import json
+d=json.loads(open("gpurun_out/bench_r2_v3.json").read().strip().splitlines()[-1])
+print(d["value"], d["ms_per_step"], d["e2e"]["ms_per_step"]); print({k:v for k,v in d["kernels_ms"].items() if v>0.15})
+PY
+tail -3 gpurun_out/bench_r2_v3.err
