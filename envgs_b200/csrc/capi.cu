@@ -51,6 +51,7 @@ int mark_visible_impl(int P, const float* means3D, const float* viewmatrix, uint
 int trace_forward_impl(Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_out& o, cudaStream_t stream);
 int trace_backward_impl(Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_grads& g, cudaStream_t stream);
 size_t trace_cache_bytes(int H, int W);
+size_t trace_cache_bytes2(int H, int W, int max_trace_depth);
 int glue_quad_vertices(int P, const float* means, const float* scales, const float* rots, float* verts, cudaStream_t stream);
 int glue_reflect_forward(const envgs_glue_camera& cam, const float* allmap, float* ref_o, float* ref_d, cudaStream_t stream);
 int glue_reflect_backward(const envgs_glue_camera& cam, const float* allmap, const float* g_ro, const float* g_rd, float* dL_dallmap, cudaStream_t stream);
@@ -206,6 +207,7 @@ void envgs_tracer_destroy(envgs_tracer* h) {
 size_t envgs_tracer_bvh_bytes(int32_t P) { return lbvh_storage_bytes(P); }
 
 size_t envgs_trace_cache_bytes(int32_t H, int32_t W) { return trace_cache_bytes(H, W); }
+size_t envgs_trace_cache_bytes2(int32_t H, int32_t W, int32_t max_trace_depth) { return trace_cache_bytes2(H, W, max_trace_depth); }
 
 static int check_glue_cam(const envgs_glue_camera* c) {
     if (!c || c->H <= 0 || c->W <= 0 || !c->K || !c->R || !c->campos) { set_error("bad glue camera"); return ENVGS_ERR_INVALID; }

@@ -30,6 +30,8 @@ struct TraceParams {
     int tiles_x;      // 8x4 tiles per row (0 => linear mapping)
     const int* ray_list;             // optional: trace only these rays (overflow fallback of the fast path) ...
     const unsigned int* ray_count;   // ... whose number lives on the device
+    int mid_half;                    // 1: this call is one segment of a segment-by-segment trace (trace_fast.cu): `mid_val` points at that
+                                     // segment's 16-float half of the row and only those 16 floats are written
 };
 
 struct HitBuf {
@@ -585,7 +587,8 @@ __global__ void __launch_bounds__(TR_THREADS) trace_kernel(const TraceParams p) 
                 o.out_aux[tidx * 2 + 0] = out_aux[0]; o.out_aux[tidx * 2 + 1] = out_aux[1];
                 float4* m4 = reinterpret_cast<float4*>(o.mid_val + tidx * 32);
 #pragma unroll
-                for (int q = 0; q < 8; q++) m4[q] = make_float4(mid[4 * q], mid[4 * q + 1], mid[4 * q + 2], mid[4 * q + 3]);
+                for (int q = 0; q < 8; q++)
+                    if (q < 4 || !p.mid_half) m4[q] = make_float4(mid[4 * q], mid[4 * q + 1], mid[4 * q + 2], mid[4 * q + 3]);
             } else {
                 const envgs_trace_grads& g = p.g;
                 g.dL_dray_o[tidx * 3 + 0] = g_ray_o.x; g.dL_dray_o[tidx * 3 + 1] = g_ray_o.y; g.dL_dray_o[tidx * 3 + 2] = g_ray_o.z;
@@ -597,7 +600,7 @@ __global__ void __launch_bounds__(TR_THREADS) trace_kernel(const TraceParams p) 
 }
 
 int launch_trace(bool bwd, Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_out* o,
-                 const envgs_trace_grads* g, const int* ray_list, const unsigned int* ray_count, cudaStream_t stream) {
+                 const envgs_trace_grads* g, const int* ray_list, const unsigned int* ray_count, cudaStream_t stream, int mid_half) {
     // launch geometry is a property of the CURRENT device: cached per device id, not once per process
     static int sm_counts[64] = {0}, occ_fs[64] = {0}, occ_bs[64] = {0};
     int dev = 0;
@@ -621,6 +624,7 @@ int launch_trace(bool bwd, Lbvh& bvh, unsigned int* counter, unsigned long long*
     p.stats = stats;
     p.ray_list = ray_list;
     p.ray_count = ray_count;
+    p.mid_half = mid_half;
     if (a.H >= 4) {
         p.tiles_x = (a.W + 7) / 8;
         p.n_items = p.tiles_x * ((a.H + 3) / 4);
@@ -641,10 +645,10 @@ int launch_trace(bool bwd, Lbvh& bvh, unsigned int* counter, unsigned long long*
 }
 
 int trace_forward_impl(Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_out& o, cudaStream_t stream) {
-    return launch_trace(false, bvh, counter, stats, a, &o, nullptr, nullptr, nullptr, stream);
+    return launch_trace(false, bvh, counter, stats, a, &o, nullptr, nullptr, nullptr, stream, 0);
 }
 int trace_backward_impl(Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_grads& g, cudaStream_t stream) {
-    return launch_trace(true, bvh, counter, stats, a, nullptr, &g, nullptr, nullptr, stream);
+    return launch_trace(true, bvh, counter, stats, a, nullptr, &g, nullptr, nullptr, stream, 0);
 }
 
 }  // namespace envgs

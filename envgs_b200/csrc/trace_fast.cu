@@ -45,6 +45,8 @@ struct FastParams {
     unsigned long long* stats;
     int n_items, tiles_x;
     int refill_threshold;         // leave an inner traversal loop when fewer lanes than this are still in it
+    int mid_half;                 // 1: one segment of a two-segment trace: mid_val is pre-offset to this segment's 16 floats, the
+                                  // other half of the row is left alone
 };
 
 constexpr int CL_THREADS = 512;               // rays per block of the class-list kernels
@@ -611,7 +613,7 @@ __device__ __forceinline__ void shade_empty_body(const FastParams& p) {
         m4[1] = make_float4(d.y, d.z, 0.0f, 0.0f);
         m4[2] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         m4[3] = make_float4(0.0f, b0, b1, b2);
-        m4[4] = m4[5] = m4[6] = m4[7] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (!p.mid_half) m4[4] = m4[5] = m4[6] = m4[7] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
 }
 
@@ -713,13 +715,13 @@ __device__ __forceinline__ void shade_fwd_body(const FastParams& p, int cls) {
             // cover one contiguous 64-byte half each
             if (VPL == 4) {
                 __stcs(reinterpret_cast<float4*>(mid + base), make_float4(mvs[0], mvs[1 % VPL], mvs[2 % VPL], mvs[3 % VPL]));
-                __stcs(reinterpret_cast<float4*>(mid + 16 + base), make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+                if (!p.mid_half) __stcs(reinterpret_cast<float4*>(mid + 16 + base), make_float4(0.0f, 0.0f, 0.0f, 0.0f));
             } else if (VPL == 2) {
                 __stcs(reinterpret_cast<float2*>(mid + base), make_float2(mvs[0], mvs[1 % VPL]));
-                __stcs(reinterpret_cast<float2*>(mid + 16 + base), make_float2(0.0f, 0.0f));
+                if (!p.mid_half) __stcs(reinterpret_cast<float2*>(mid + 16 + base), make_float2(0.0f, 0.0f));
             } else {
                 __stcs(mid + base, mvs[0]);
-                __stcs(mid + 16 + base, 0.0f);
+                if (!p.mid_half) __stcs(mid + 16 + base, 0.0f);
             }
         }
     }
@@ -985,10 +987,13 @@ __global__ void __launch_bounds__(SBWD_THREADS, SBWD_MINBLOCKS) shade_bwd_kernel
 // host side
 // ------------------------------------------------------------------------------------------------------
 int launch_trace(bool bwd, Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_out* o,
-                 const envgs_trace_grads* g, const int* ray_list, const unsigned int* ray_count, cudaStream_t stream);
+                 const envgs_trace_grads* g, const int* ray_list, const unsigned int* ray_count, cudaStream_t stream, int mid_half);
 
 bool trace_fast_eligible(const envgs_trace_args& a, const void* cache) {
-    if (cache == nullptr || a.max_trace_depth != 0 || a.start_from_first != 0) return false;
+    // max_trace_depth 1 runs segment by segment (trace_forward_fast / trace_backward_fast dispatch on it); its second segment
+    // only exists when the traced set carries a specular channel
+    if (cache == nullptr || a.start_from_first != 0 || a.max_trace_depth > 1) return false;
+    if (a.max_trace_depth == 1 && a.others_precomp == nullptr) return false;
     const char* f = getenv("ENVGS_TRACE_FORCE_MONOLITHIC");
     return !(f && f[0] == '1');
 }
@@ -997,8 +1002,8 @@ bool trace_fast_eligible(const envgs_trace_args& a, const void* cache) {
 // (they write disjoint rays); the caller's stream joins before returning control.
 struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; };
 
-int trace_forward_fast(Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_out& o,
-                       void* cache, cudaStream_t stream, const SideStream& side) {
+static int trace_forward_segment(Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_out& o,
+                                 void* cache, cudaStream_t stream, const SideStream& side, int mid_half) {
     static int sm_counts[64] = {0}, occs[64] = {0};   // per device id (the handle may live on any GPU of the process)
     int dev = 0;
     ENVGS_CUDA_TRY(cudaGetDevice(&dev));
@@ -1017,6 +1022,7 @@ int trace_forward_fast(Lbvh& bvh, unsigned int* counter, unsigned long long* sta
     carve_cache((char*)cache, a.H, a.W, p);
     p.work_counter = counter;
     p.stats = stats;
+    p.mid_half = mid_half;
     {
         const char* e = getenv("ENVGS_TRACE_REFILL");
         p.refill_threshold = e ? atoi(e) : 28;
@@ -1040,7 +1046,7 @@ int trace_forward_fast(Lbvh& bvh, unsigned int* counter, unsigned long long* sta
     // fills every SM for its whole duration, starts.
     ENVGS_CUDA_TRY(cudaEventRecord(side.fork, stream));
     ENVGS_CUDA_TRY(cudaStreamWaitEvent(side.stream, side.fork, 0));
-    int rc = launch_trace(false, bvh, counter, stats, a, &o, nullptr, p.overflow_list, p.overflow_count, side.stream);
+    int rc = launch_trace(false, bvh, counter, stats, a, &o, nullptr, p.overflow_list, p.overflow_count, side.stream, mid_half);
     if (rc != ENVGS_OK) return rc;
     {
         ENVGS_TIMED("trace_class_lists", stream);
@@ -1061,11 +1067,12 @@ int trace_forward_fast(Lbvh& bvh, unsigned int* counter, unsigned long long* sta
     return ENVGS_OK;
 }
 
-int trace_backward_fast(Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_grads& g,
-                        void* cache, cudaStream_t stream, const SideStream& side) {
+static int trace_backward_segment(Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_grads& g,
+                                  void* cache, cudaStream_t stream, const SideStream& side, int mid_half) {
     FastParams p;
     memset(&p, 0, sizeof(p));
     p.nodes = bvh.nodes; p.prims = bvh.prims; p.a = a; p.g = g;
+    p.mid_half = mid_half;
     carve_cache((char*)cache, a.H, a.W, p);
     const size_t R = (size_t)a.H * a.W;
     int sm_count = 148;
@@ -1075,7 +1082,7 @@ int trace_backward_fast(Lbvh& bvh, unsigned int* counter, unsigned long long* st
     ENVGS_CUDA_TRY(cudaMemsetAsync(g.dL_dray_d, 0, R * 3 * sizeof(float), stream));
     ENVGS_CUDA_TRY(cudaEventRecord(side.fork, stream));
     ENVGS_CUDA_TRY(cudaStreamWaitEvent(side.stream, side.fork, 0));
-    int rc = launch_trace(true, bvh, counter, stats, a, nullptr, &g, p.overflow_list, p.overflow_count, side.stream);
+    int rc = launch_trace(true, bvh, counter, stats, a, nullptr, &g, p.overflow_list, p.overflow_count, side.stream, mid_half);
     if (rc != ENVGS_OK) return rc;
     ENVGS_CUDA_TRY(cudaEventRecord(side.join, side.stream));
     {
@@ -1091,6 +1098,234 @@ int trace_backward_fast(Lbvh& bvh, unsigned int* counter, unsigned long long* st
         ENVGS_LAUNCH_CHECK("trace_shade_bwd16", false, stream);
     }
     ENVGS_CUDA_TRY(cudaStreamWaitEvent(stream, side.join, 0));
+    return ENVGS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// two segments (max_trace_depth = 1), segment by segment on the hit-parallel kernels
+// ------------------------------------------------------------------------------------------------------
+// tracePath (TRACE/optix_tracer/forward.cu:453-559, backward.cu:890-1086) restated at the granularity of whole segments:
+//   forward : segment 0 on the given rays -> per ray: continue? (|N0| != 0 and spec0 > threshold) -> reflected ray
+//             (d1 = d0 - 2 (n.d0) n, o1 = o0 + D0 d0 + 1e-5 d1) -> segment 1 on those rays -> rgb = C0 (1 - spec0) + spec0 C1
+//   backward: segment 1 with dL/dC1 = spec0 dL/drgb -> its ray gradient is folded into segment 0's upstream
+//             (dL/dD0, dL/dN0, dL/dspec0) and into the running ray gradient -> segment 0 -> ray gradient += carried part.
+// Each segment is the single-segment fast path above (traverse -> class lists -> hit-parallel shading, general kernel for the
+// >= 16-hit rays), with its own hit cache; rays that do not continue carry NaN into segment 1, find no hit and cost one box test.
+// Scratch layout behind the two hit caches (floats): see trace_cache_bytes2.
+struct Seg2Scratch {
+    float *ray1_o, *ray1_d;                                   // R x 3 each
+    float *o1_rgb, *o1_dpt, *o1_acc, *o1_norm, *o1_dist, *o1_aux;   // segment-1 outputs nobody reads (its mid_val half is what counts)
+    float *g_rgb1, *zeros;                                    // backward: upstream of segment 1; R x 3 zeros for its other inputs
+    float *g_o1, *g_d1;                                       // segment 1's ray gradient
+    float *u_rgb, *u_dpt, *u_norm, *u_aux, *base_d;           // segment 0's upstream + carried direction gradient
+    void *cache0, *cache1;
+};
+
+size_t trace_cache_bytes2(int H, int W, int max_trace_depth) {
+    if (max_trace_depth <= 0) return trace_cache_bytes(H, W);
+    const size_t R = (size_t)H * W, c = align_up(trace_cache_bytes(H, W), 256);
+    return 2 * c + align_up(R * 24 * sizeof(float), 256) + 256;    // max(forward 19 R, backward 24 R) floats of scratch
+}
+
+static Seg2Scratch carve_seg2(void* cache, int H, int W) {
+    Seg2Scratch s;
+    const size_t R = (size_t)H * W, c = align_up(trace_cache_bytes(H, W), 256);
+    char* b = (char*)cache;
+    s.cache0 = b; s.cache1 = b + c;
+    float* f = reinterpret_cast<float*>(b + 2 * c);
+    // forward use                               // backward use of the same region
+    s.ray1_o = f; s.ray1_d = f + 3 * R;          s.g_rgb1 = f; s.zeros = f + 3 * R;
+    s.o1_rgb = f + 6 * R; s.o1_dpt = f + 9 * R;  s.g_o1 = f + 6 * R; s.g_d1 = f + 9 * R;
+    s.o1_acc = f + 10 * R; s.o1_norm = f + 11 * R; s.o1_dist = f + 14 * R; s.o1_aux = f + 17 * R;   // ends at 19 R
+    s.u_rgb = f + 12 * R; s.u_dpt = f + 15 * R; s.u_norm = f + 16 * R; s.u_aux = f + 19 * R; s.base_d = f + 21 * R;   // ends at 24 R
+    return s;
+}
+
+__device__ __forceinline__ bool seg_continues(const float* mid0, float thr, float3& N0) {
+    N0 = f3(mid0[MID_NORM], mid0[MID_NORM + 1], mid0[MID_NORM + 2]);
+    return !(length3(N0) == 0.0f || mid0[MID_AUX] <= thr);                  // forward.cu:551
+}
+
+__global__ void __launch_bounds__(256) seg1_rays_kernel(int R, const float* __restrict__ mid_val, float thr, float* __restrict__ ray1_o,
+                                                         float* __restrict__ ray1_d) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const float* m = mid_val + (size_t)r * 32;
+    float3 N0;
+    float3 o1 = f3(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000), __int_as_float(0x7fc00000)), d1 = o1;   // NaN: no traversal
+    if (seg_continues(m, thr, N0)) {
+        const float3 ray_ot = f3(m[MID_RAYO], m[MID_RAYO + 1], m[MID_RAYO + 2]);
+        float3 ray_dt = f3(m[MID_RAYD], m[MID_RAYD + 1], m[MID_RAYD + 2]);
+        const float3 E = ray_ot + m[MID_DPT] * ray_dt;                      // forward.cu:447, :553-557
+        const float3 n = normalize3(N0);
+        ray_dt = ray_dt - 2.0f * dot(n, ray_dt) * n;
+        o1 = E + TR_STEP_EPSILON * ray_dt;
+        d1 = ray_dt;
+    }
+    ray1_o[3 * (size_t)r] = o1.x; ray1_o[3 * (size_t)r + 1] = o1.y; ray1_o[3 * (size_t)r + 2] = o1.z;
+    ray1_d[3 * (size_t)r] = d1.x; ray1_d[3 * (size_t)r + 1] = d1.y; ray1_d[3 * (size_t)r + 2] = d1.z;
+}
+
+__global__ void __launch_bounds__(256) seg2_combine_kernel(int R, float* __restrict__ mid_val, float thr, float* __restrict__ out_rgb) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    float* m = mid_val + (size_t)r * 32;
+    float3 N0;
+    const bool cont = seg_continues(m, thr, N0);
+    float s_prod = 1.0f;
+    const float f0 = 1.0f - m[MID_AUX];                                     // forward.cu:523-528 with max_trace_depth = 1
+    float rgb[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) rgb[ch] = 0.0f + m[MID_RGB + ch] * f0 * s_prod;
+    s_prod *= m[MID_AUX];
+    if (cont) {
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) rgb[ch] += m[16 + MID_RGB + ch] * 1.0f * s_prod;
+    } else {
+        float4* z = reinterpret_cast<float4*>(m + 16);                       // the path stopped: no second segment was recorded
+        z[0] = z[1] = z[2] = z[3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+    out_rgb[3 * (size_t)r] = rgb[0]; out_rgb[3 * (size_t)r + 1] = rgb[1]; out_rgb[3 * (size_t)r + 2] = rgb[2];
+}
+
+// backward.cu:915-1023 for two segments.  Segment 1's upstream colour gradient.
+__global__ void __launch_bounds__(256) seg2_bwd_prep1_kernel(int R, const float* __restrict__ mid_val, const float* __restrict__ dLo_rgb,
+                                                              float* __restrict__ g_rgb1, float* __restrict__ zeros) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const float s_prod = mid_val[(size_t)r * 32 + MID_AUX];                 // s_prod after the bookkeeping loop = spec0; f_this = 1
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) {
+        g_rgb1[3 * (size_t)r + ch] = dLo_rgb[3 * (size_t)r + ch] * 1.0f * s_prod;
+        zeros[3 * (size_t)r + ch] = 0.0f;
+    }
+}
+
+// Segment 0's upstream (colour, depth, normal, aux) and the ray gradient carried over from segment 1.
+__global__ void __launch_bounds__(256) seg2_bwd_prep0_kernel(int R, const float* __restrict__ mid_val, float thr, const float* __restrict__ out_rgb,
+                                                              const float* __restrict__ dLo_rgb, const float* __restrict__ dLo_dpt,
+                                                              const float* __restrict__ dLo_norm, const float* __restrict__ dLo_aux,
+                                                              const float* __restrict__ g_o1, const float* __restrict__ g_d1,
+                                                              float* __restrict__ u_rgb, float* __restrict__ u_dpt, float* __restrict__ u_norm,
+                                                              float* __restrict__ u_aux, float* __restrict__ base_d) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const float* m = mid_val + (size_t)r * 32;
+    const float seg_aux0 = m[MID_AUX];
+    const float3 seg_norm = f3(m[MID_NORM], m[MID_NORM + 1], m[MID_NORM + 2]);
+    const float3 ray_dt = f3(m[MID_RAYD], m[MID_RAYD + 1], m[MID_RAYD + 2]);
+    const float seg_dpt = m[MID_DPT];
+    float3 g_ray_o = ld3(g_o1, r), g_ray_d = ld3(g_d1, r);
+    float dL_ddpt = 0.0f, dL_daux0 = 0.0f;
+    float3 dL_dnorm = f3(0, 0, 0);
+    const float f_this = 1.0f - seg_aux0;
+    // The reference divides its running specular product by spec0 only when it actually walks segment 1 (`s_prod /= s_prev` sits
+    // behind the `continue`, backward.cu:955-957, :988): a ray that stopped after its first segment therefore back-propagates
+    // its colour scaled by spec0.  Reproduced, not corrected (parity).
+    float3 N0;
+    const float s_prod = seg_continues(m, thr, N0) ? seg_aux0 / seg_aux0 : seg_aux0;
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) {
+        const float go = dLo_rgb[3 * (size_t)r + ch];
+        u_rgb[3 * (size_t)r + ch] = go * f_this * s_prod;
+        // C_prev after the suffix bookkeeping (backward.cu:915-935): out_rgb + 1 * (0 - C0)
+        const float C_prev = out_rgb[3 * (size_t)r + ch] + 1.0f * (0.0f - m[MID_RGB + ch]);
+        dL_daux0 += go * (C_prev / seg_aux0);
+    }
+    if (length3(seg_norm) != 0.0f) {                                        // backward.cu:1003-1021
+        g_ray_d = g_ray_d + g_ray_o * TR_STEP_EPSILON;
+        const float3 n = normalize3(seg_norm);
+        dL_ddpt += sum3(g_ray_o * ray_dt);
+        const float3 up = g_ray_d * -2.0f;
+        const float dotnd = dot(n, ray_dt);
+        const float3 dn = f3(up.x * (dotnd + ray_dt.x * n.x) + up.y * ray_dt.x * n.y + up.z * ray_dt.x * n.z,
+                             up.x * ray_dt.y * n.x + up.y * (dotnd + ray_dt.y * n.y) + up.z * ray_dt.y * n.z,
+                             up.x * ray_dt.z * n.x + up.y * ray_dt.z * n.y + up.z * (dotnd + ray_dt.z * n.z));
+        dL_dnorm += dnormvdv(seg_norm, dn);
+        const float3 dd = f3(up.x * n.x * n.x + up.y * n.x * n.y + up.z * n.x * n.z,
+                             up.x * n.y * n.x + up.y * n.y * n.y + up.z * n.y * n.z,
+                             up.x * n.z * n.x + up.y * n.z * n.y + up.z * n.z * n.z);
+        g_ray_d = g_ray_o * seg_dpt + g_ray_d + dd;
+    }
+    u_dpt[r] = dL_ddpt + dLo_dpt[r];
+    const float3 gn = dL_dnorm + ld3(dLo_norm, r);
+    u_norm[3 * (size_t)r] = gn.x; u_norm[3 * (size_t)r + 1] = gn.y; u_norm[3 * (size_t)r + 2] = gn.z;
+    u_aux[2 * (size_t)r] = dL_daux0 + dLo_aux[2 * (size_t)r];
+    u_aux[2 * (size_t)r + 1] = dLo_aux[2 * (size_t)r + 1];
+    base_d[3 * (size_t)r] = g_ray_d.x; base_d[3 * (size_t)r + 1] = g_ray_d.y; base_d[3 * (size_t)r + 2] = g_ray_d.z;
+}
+
+__global__ void __launch_bounds__(256) seg2_bwd_finish_kernel(int R, const float* __restrict__ g_o1, const float* __restrict__ base_d,
+                                                               float* __restrict__ dL_dray_o, float* __restrict__ dL_dray_d) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (size_t)R * 3) return;
+    dL_dray_o[e] += g_o1[e];
+    dL_dray_d[e] += base_d[e];
+}
+
+int trace_forward_fast(Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_out& o,
+                       void* cache, cudaStream_t stream, const SideStream& side) {
+    if (a.max_trace_depth == 0) return trace_forward_segment(bvh, counter, stats, a, o, cache, stream, side, 0);
+    const int R = a.H * a.W, nb = (R + 255) / 256;
+    Seg2Scratch sc = carve_seg2(cache, a.H, a.W);
+    envgs_trace_args a0 = a;
+    a0.max_trace_depth = 0;
+    int rc = trace_forward_segment(bvh, counter, stats, a0, o, sc.cache0, stream, side, 1);      // writes mid_val[0:16], out_* of segment 0
+    if (rc != ENVGS_OK) return rc;
+    {
+        ENVGS_TIMED("trace_seg_glue", stream);
+        seg1_rays_kernel<<<nb, 256, 0, stream>>>(R, o.mid_val, a.specular_threshold, sc.ray1_o, sc.ray1_d);
+        ENVGS_LAUNCH_CHECK("seg1_rays", false, stream);
+    }
+    envgs_trace_args a1 = a0;
+    a1.ray_o = sc.ray1_o; a1.ray_d = sc.ray1_d;
+    envgs_trace_out o1 = o;
+    o1.out_rgb = sc.o1_rgb; o1.out_dpt = sc.o1_dpt; o1.out_acc = sc.o1_acc; o1.out_norm = sc.o1_norm; o1.out_dist = sc.o1_dist;
+    o1.out_aux = sc.o1_aux; o1.mid_val = o.mid_val + 16;                                         // a_weights: both segments accumulate
+    rc = trace_forward_segment(bvh, counter, stats, a1, o1, sc.cache1, stream, side, 1);
+    if (rc != ENVGS_OK) return rc;
+    {
+        ENVGS_TIMED("trace_seg_glue", stream);
+        seg2_combine_kernel<<<nb, 256, 0, stream>>>(R, o.mid_val, a.specular_threshold, o.out_rgb);
+        ENVGS_LAUNCH_CHECK("seg2_combine", false, stream);
+    }
+    return ENVGS_OK;
+}
+
+int trace_backward_fast(Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_grads& g,
+                        void* cache, cudaStream_t stream, const SideStream& side) {
+    if (a.max_trace_depth == 0) return trace_backward_segment(bvh, counter, stats, a, g, cache, stream, side, 0);
+    const int R = a.H * a.W, nb = (R + 255) / 256;
+    Seg2Scratch sc = carve_seg2(cache, a.H, a.W);
+    envgs_trace_args a0 = a;
+    a0.max_trace_depth = 0;
+    {
+        ENVGS_TIMED("trace_seg_glue", stream);
+        seg2_bwd_prep1_kernel<<<nb, 256, 0, stream>>>(R, g.mid_val, g.dL_drgb, sc.g_rgb1, sc.zeros);
+        ENVGS_LAUNCH_CHECK("seg2_bwd_prep1", false, stream);
+    }
+    // segment 1: rays and saved state come from its half of mid_val; only its colour has an upstream gradient
+    envgs_trace_grads g1 = g;
+    g1.mid_val = g.mid_val + 16;
+    g1.dL_drgb = sc.g_rgb1; g1.dL_ddpt = sc.zeros; g1.dL_dacc = sc.zeros; g1.dL_dnorm = sc.zeros; g1.dL_ddist = sc.zeros; g1.dL_daux = sc.zeros;
+    g1.dL_dray_o = sc.g_o1; g1.dL_dray_d = sc.g_d1;
+    int rc = trace_backward_segment(bvh, counter, stats, a0, g1, sc.cache1, stream, side, 1);
+    if (rc != ENVGS_OK) return rc;
+    {
+        ENVGS_TIMED("trace_seg_glue", stream);
+        seg2_bwd_prep0_kernel<<<nb, 256, 0, stream>>>(R, g.mid_val, a.specular_threshold, g.out_rgb, g.dL_drgb, g.dL_ddpt, g.dL_dnorm, g.dL_daux, sc.g_o1, sc.g_d1,
+                                                      sc.u_rgb, sc.u_dpt, sc.u_norm, sc.u_aux, sc.base_d);
+        ENVGS_LAUNCH_CHECK("seg2_bwd_prep0", false, stream);
+    }
+    envgs_trace_grads g0 = g;
+    g0.dL_drgb = sc.u_rgb; g0.dL_ddpt = sc.u_dpt; g0.dL_dnorm = sc.u_norm; g0.dL_daux = sc.u_aux;
+    rc = trace_backward_segment(bvh, counter, stats, a0, g0, sc.cache0, stream, side, 1);
+    if (rc != ENVGS_OK) return rc;
+    {
+        ENVGS_TIMED("trace_seg_glue", stream);
+        seg2_bwd_finish_kernel<<<(unsigned)(((size_t)R * 3 + 255) / 256), 256, 0, stream>>>(R, sc.g_o1, sc.base_d, g.dL_dray_o, g.dL_dray_d);
+        ENVGS_LAUNCH_CHECK("seg2_bwd_finish", false, stream);
+    }
     return ENVGS_OK;
 }
 

@@ -7,6 +7,7 @@ libenvgs_b200.so (`envgs_tracer_*`, `envgs_trace_forward/backward`).
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import NamedTuple
 
 import torch
@@ -183,8 +184,10 @@ class _TraceSurfels(torch.autograd.Function):
         # scratch for the hit-parallel fast path (per-ray hit lists, re-used by backward); the library falls back to the
         # general kernel when the call shape is not eligible
         hit_cache = None
-        if int(s.max_trace_depth) == 0 and not start_from_first:
-            hit_cache = torch.empty(int(L.envgs_trace_cache_bytes(H, W)), dtype=torch.uint8, device=device)
+        depth = int(s.max_trace_depth)
+        if not start_from_first and (depth == 0 or (depth == 1 and oth is not None and oth.numel())) \
+                and os.environ.get("ENVGS_TRACE_NO_CACHE") != "1":
+            hit_cache = torch.empty(int(L.envgs_trace_cache_bytes2(H, W, depth)), dtype=torch.uint8, device=device)
 
         args = _trace_args(P, H, W, s, training, start_from_first, ro, rd, bg, m3, sh, col, oth, opa, sc, rot, vm, pm, cam)
         out = _lib.TraceOut(_lib.ptr(out_rgb), _lib.ptr(out_dpt), _lib.ptr(out_acc), _lib.ptr(out_norm), _lib.ptr(out_dist),

@@ -210,12 +210,14 @@ typedef struct envgs_trace_out {   /* all written for every ray; a_weights accum
     float* out_aux;   /* (H,W,2)  */
     float* mid_val;   /* (H,W,32) fully written */
     float* a_weights; /* (P,1) or NULL when !training */
-    void* hit_cache;  /* optional scratch of envgs_trace_cache_bytes(H,W) bytes: enables the hit-parallel fast path for
-                         max_trace_depth == 0 && !start_from_first and carries the per-ray hit lists to the backward call;
-                         NULL selects the general (monolithic) kernel */
+    void* hit_cache;  /* optional scratch of envgs_trace_cache_bytes2(H, W, max_trace_depth) bytes: enables the hit-parallel fast
+                         path for !start_from_first (one segment, or two segments traced one after the other when
+                         max_trace_depth == 1 and others_precomp is given) and carries the per-ray hit lists to the backward
+                         call; NULL selects the general (monolithic) kernel */
 } envgs_trace_out;
 
-size_t envgs_trace_cache_bytes(int32_t H, int32_t W);
+size_t envgs_trace_cache_bytes(int32_t H, int32_t W);                              /* = envgs_trace_cache_bytes2(H, W, 0) */
+size_t envgs_trace_cache_bytes2(int32_t H, int32_t W, int32_t max_trace_depth);
 
 int envgs_trace_forward(envgs_tracer* h, const envgs_trace_args* args, const envgs_trace_out* out, void* stream);
 

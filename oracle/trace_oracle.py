@@ -19,6 +19,7 @@ Backward comes from autograd, with the reference's deviations reproduced (backwa
     quad-vertex form (:293-306, :319-334) — while the accumulated normal uses R[:,2]
   * no gradient for `dist` (:796) and, unless start_from_first, none for `acc` (:792-796)
   * non-zero background would be counted twice in dL/dalpha by the reference (:769-772); use bg = 0 when comparing
+  * two segments: a ray whose second segment is skipped back-propagates its first colour scaled by spec_0 (:955-957, :988)
 Third-party arithmetic outside /root/reference: the ray/triangle distance `t` comes from NVIDIA OptiX 7.7 (closed
 source, driver-side libnvoptix; headers vendored at third_party/optix @ 7b5c4e86).  Its specification here is the
 analytic ray-plane distance the reference's own backward differentiates (backward.cu:293-302).
@@ -243,12 +244,19 @@ def trace(ray_o, ray_d, means3D, opacities, scales, rotations, shs=None, colors_
             out_acc = A if start_from_first else A.detach()
             out_dist = dist.detach()
         f_this = torch.ones_like(s_prod) if i == max_trace_depth else 1.0 - O[:, 0]
-        rgb = rgb + a[:, None] * Cc * (f_this * s_prod)[:, None]
+        nlen = Nn.norm(dim=-1)
+        cont = active & (nlen != 0) & (O[:, 0] > specular_threshold)
+        Cc_bp = Cc
+        if i < max_trace_depth:
+            # Reference deviation (backward.cu:955-957, :988): the running specular product is divided by spec_i only when the
+            # NEXT segment is actually walked, so a ray that stops here back-propagates its colour scaled by spec_i.  Value
+            # unchanged, gradient of the colour scaled.
+            q = torch.where(active & ~cont, O[:, 0].detach(), torch.ones_like(s_prod))
+            Cc_bp = Cc.detach() + (Cc - Cc.detach()) * q[:, None]
+        rgb = rgb + a[:, None] * Cc_bp * (f_this * s_prod)[:, None]
         s_prod = s_prod * torch.where(active, O[:, 0], torch.ones_like(s_prod))
         seg = torch.cat([o, d, D[:, None], A[:, None], Nn, O, Cc], dim=-1) * a[:, None]
         mids.append(seg)
-        nlen = Nn.norm(dim=-1)
-        cont = active & (nlen != 0) & (O[:, 0] > specular_threshold)
         if i == max_trace_depth:
             break
         nsafe = torch.where(cont[:, None], Nn, torch.ones_like(Nn))

@@ -152,3 +152,27 @@ def test_fast_path_equals_general_kernel(built_lib, monkeypatch):
     for k in ("g_means", "g_opac", "g_scales", "g_rots", "g_shs", "g_ray_o", "g_ray_d"):
         assert Hh.rel_l2(fast[k], gen[k]) < 2e-4, f"{k}: {Hh.rel_l2(fast[k], gen[k]):.3e}"
     assert Hh.rel_l2(fast["wet"].reshape(-1), gen["wet"].reshape(-1)) < 1e-5
+
+
+def test_two_segment_fast_path_equals_general_kernel(built_lib, monkeypatch):
+    """max_trace_depth = 1 runs segment by segment on the hit-parallel kernels (trace_fast.cu, trace_forward_fast); the same call
+    through the general kernel (ENVGS_TRACE_FORCE_MONOLITHIC=1), which walks both segments of a ray in one thread, must agree
+    — including rays that stop after the first segment and the dense rays that overflow into the 16-hit chunk loop."""
+    env = scene.make_env_set(6000, seed=9, s0=0.09)
+    env.specular.copy_(torch.rand(env.specular.shape, generator=torch.Generator().manual_seed(1)) * 0.9)   # some below the threshold
+    cam = scene.ring_cameras(1, 36, 52, seed=2)[0]
+    ro, rd = Hh.synthetic_rays(36, 52, seed=8)
+    up = _up(36, 52, 70)
+    kw = dict(use_sh=True, others=True, max_trace_depth=1, specular_threshold=0.3, grads=up)
+    fast = Hh.run_cuda_trace(env, cam, ro, rd, **kw)
+    monkeypatch.setenv("ENVGS_TRACE_FORCE_MONOLITHIC", "1")
+    gen = Hh.run_cuda_trace(env, cam, ro, rd, **kw)
+    monkeypatch.delenv("ENVGS_TRACE_FORCE_MONOLITHIC")
+    stopped = gen["mid"][..., 16:].abs().sum(-1) == 0
+    assert 0.02 < float(stopped.float().mean()) < 0.98          # both kinds of ray are present
+    assert torch.equal(stopped, fast["mid"][..., 16:].abs().sum(-1) == 0)
+    for k in ("rgb", "dpt", "acc", "norm", "aux", "mid", "dist"):
+        assert Hh.frac_above(fast[k], gen[k], 1e-5 * max(1.0, float(gen[k].abs().max()))) < 1e-4, Hh.image_report(k, fast[k], gen[k], 1e-5)
+    for k in ("g_means", "g_opac", "g_scales", "g_rots", "g_shs", "g_others", "g_ray_o", "g_ray_d"):
+        assert Hh.rel_l2(fast[k], gen[k]) < 2e-4, f"{k}: {Hh.rel_l2(fast[k], gen[k]):.3e}"
+    assert Hh.rel_l2(fast["wet"].reshape(-1), gen["wet"].reshape(-1)) < 1e-5

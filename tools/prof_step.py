@@ -14,7 +14,7 @@ def main():
     stats = "--stats" in sys.argv
     Pb, Pe, H, W = bench.WORKLOADS[wl]
     dev = torch.device("cuda")
-    s0 = 0.005 if H >= 1080 else 0.005 * 1080 / H
+    s0 = 0.005 * 1080 / H
     base = scene.make_base_set(Pb, seed=0, s0=s0)
     env = scene.make_env_set(Pe, seed=1, s0=s0) if Pe else None
     r = EnvGSRenderer(base, env, device=dev)
