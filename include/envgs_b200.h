@@ -174,7 +174,8 @@ int envgs_tracer_build(envgs_tracer* h, const float* vertices, int32_t num_verti
 size_t envgs_tracer_bvh_bytes(int32_t P);
 
 /* Debug aid (synchronises the device): read and clear the traversal counters
- * [rays, nodes visited, quad tests, hits inserted, 16-hit chunks, contributions, 0, 0] and switch counting on/off. */
+ * [rays, nodes visited, quad tests, hits stored, 16-hit chunks, quad hits found (fast path) / contributions (general kernel), 0, 0]
+ * and switch counting on/off. */
 int envgs_debug_trace_stats(envgs_tracer* h, int32_t enable, uint64_t out[8]);
 
 typedef struct envgs_trace_args {

@@ -1,3 +1,7 @@
-python oracle/make_golden.py --trace-only --only=trace_ref_two_segments_stop 2>&1 | tail -2
-cp gpurun_out/golden/trace_ref_two_segments_stop.pt tests/golden/
-python -m pytest tests/test_gpu_golden.py tests/test_oracle_golden.py -q --tb=line -k "stop" 2>&1 | tail -8
+python -m pytest tests -m gpu -q --tb=short -x -k "trace or tracer or pipeline or golden" 2>&1 | tail -6
+python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-ref-gpu > gpurun_out/bench_r2_v4.json 2> gpurun_out/bench_r2_v4.err; python - <<'PY'
+import json
+d=json.loads(open("gpurun_out/bench_r2_v4.json").read().strip().splitlines()[-1])
+print(d["value"], d["ms_per_step"], d["e2e"]["ms_per_step"]); print({k:v for k,v in d["kernels_ms"].items() if v>0.15}); print(d["roofline"].get("composited_hits"))
+PY
+tail -3 gpurun_out/bench_r2_v4.err
