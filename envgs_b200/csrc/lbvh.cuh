@@ -56,6 +56,18 @@ struct Lbvh {
     float* bounds = nullptr;       // 6 floats: scene lo/hi (as ordered ints during reduction)
     char* sort_temp = nullptr;
     size_t sort_temp_bytes = 0;
+    // PLOC builder state (lbvh.cu): two cluster arrays (ping-pong), nearest-neighbour indices, validity flags + their scan
+    float4* cl_lo[2] = {nullptr, nullptr};
+    float4* cl_hi[2] = {nullptr, nullptr};
+    int* cl_link[2] = {nullptr, nullptr};    // child link of the cluster's root (>= 0 node id, < 0 ~surfel id)
+    int* cl_slot[2] = {nullptr, nullptr};    // index into parent[] of the cluster's root
+    int* cl_nn = nullptr;
+    int* cl_valid = nullptr;
+    int* cl_scan = nullptr;
+    int* cl_counter = nullptr;               // [0] merges done so far, [1] clusters alive after compaction
+    char* scan_temp = nullptr;
+    size_t scan_temp_bytes = 0;
+    int full_builds = 0, calls_since_full = 1 << 30;   // topology-reuse policy (lbvh_build)
 };
 
 size_t lbvh_storage_bytes(int P);

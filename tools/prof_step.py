@@ -21,6 +21,8 @@ def main():
     cams = [c.to(dev) for c in scene.ring_cameras(4, H, W, seed=2)]
     target = torch.rand(H, W, 3, device=dev)
     if stats and Pe:
+        with torch.no_grad():
+            r(cams[0], target)            # builds the BVH (the native handle is created lazily on the first build)
         _lib.lib().envgs_debug_trace_stats(r.tracer.optix_context.handle, 1, None)
     for s in range(steps):
         for p in r.parameters(): p.grad = None
