@@ -193,6 +193,10 @@ __device__ __forceinline__ void sh_dir_grad(int deg, float3 d, const float* sh, 
 // then taken on identical bits.  Forward and backward kernels use the same helpers, so they always agree with each other.
 // -DENVGS_FAST_MATH selects the 1-instruction MUFU forms (rcp.approx / ex2.approx, <= 2 ulp): render kernels 14-17 % faster,
 // gradients still within 8e-5 relative L2, but ~3 of 2 M pixels flip an alpha >= 1/255 decision (colour error up to 1e-3).
+// px_rcp_v: reciprocal for VALUE-only uses (distortion depth mapping, the backward's T / (1 - alpha), 1 / p.z in the chain rule):
+// no alpha / T / branch decision reads these, so the 1-ulp MUFU form only moves gradients and the distortion map by ~1e-7 relative.
+// Every quantity a decision depends on (s = p.xy / p.z -> rho -> alpha) goes through px_div / px_exp below.
+__device__ __forceinline__ float px_rcp_v(float x) { return __fdividef(1.0f, x); }
 #ifdef ENVGS_FAST_MATH
 __device__ __forceinline__ float px_rcp(float x) { return __fdividef(1.0f, x); }
 __device__ __forceinline__ float px_exp(float x) { return __expf(x); }

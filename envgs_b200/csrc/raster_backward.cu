@@ -173,8 +173,8 @@ __global__ void __launch_bounds__(256, RBWD_MINBLOCKS) render_bwd_kernel(
                 const float tau = st.r3[sj].w;                   // the forward kernel's early reject, same expression, same bits
                 const bool reject = (p.x * p.x + p.y * p.y > tau * (p.z * p.z)) && (rho2d > tau);
                 if (!reject && p.z != 0.0f) {
-                    const float rz = px_rcp(p.z);                // same reciprocal form as the forward kernel
-                    float sx = px_div(p.x, p.z, rz), sy = px_div(p.y, p.z, rz);
+                    const float rz = px_rcp_v(p.z);              // value-only use below (chain rule through s = p.xy / p.z)
+                    float sx = px_div(p.x, p.z, rz), sy = px_div(p.y, p.z, rz);   // the forward kernel's own division: same alpha, same branch
                     float rho3d = sx * sx + sy * sy;
                     float rho = fminf(rho3d, rho2d);
                     float c_d = (rho3d <= rho2d) ? (sx * Tw.x + sy * Tw.y) + Tw.z : Tw.z;
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(256, RBWD_MINBLOCKS) render_bwd_kernel(
                         if (alpha >= ALPHA_MIN) {
                             contrib = true;
                             const float4 r3 = st.r3[sj];
-                            const float r1ma = px_rcp(1.0f - alpha);
+                            const float r1ma = px_rcp_v(1.0f - alpha);
                             T = T * r1ma;
                             const float w = alpha * T;
                             float dL_dalpha = 0.0f;
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(256, RBWD_MINBLOCKS) render_bwd_kernel(
                                 g[ch] = w * dL_dpixel[ch];
                             }
                             float dL_dz = 0.0f, dL_dweight = 0.0f;
-                            const float rcd = px_rcp(c_d);
+                            const float rcd = px_rcp_v(c_d);
                             const float m_d = FAR_N / (FAR_N - NEAR_N) * (1.0f - NEAR_N * rcd);
                             const float dmd_dd = (FAR_N * NEAR_N) / (FAR_N - NEAR_N) * rcd * rcd;
                             if (pos == median_contributor) dL_dz += dL_dmedian_depth;

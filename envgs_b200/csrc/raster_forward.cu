@@ -444,7 +444,7 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(
                                 w = alpha * T;
                                 const float4 r3 = st.r3[sj];
                                 float A = 1.0f - T;
-                                float m = FAR_N / (FAR_N - NEAR_N) * (1.0f - px_div(NEAR_N, depth, px_rcp(depth)));
+                                float m = FAR_N / (FAR_N - NEAR_N) * (1.0f - NEAR_N * px_rcp_v(depth));
                                 distortion += (m * m * A + M2 - 2.0f * m * M1) * w;
                                 Dacc += depth * w;
                                 M1 += m * w;

@@ -688,7 +688,7 @@ __device__ __forceinline__ void shade_fwd_body(const FastParams& p, int cls) {
         const float T_final = eval_and_scan<L>(a, valid, hit_t, hit_id, ray_o, ray_d, basis, nbasis, sh_vec4, campos, h, e);
 
         // distortion bookkeeping needs exclusive prefix sums of w*m and w*m^2 (forward.cu:405-409)
-        const float m = FAR_N / (FAR_N - NEAR_N) * (1.0f - NEAR_N * px_rcp(e.cmd));
+        const float m = FAR_N / (FAR_N - NEAR_N) * (1.0f - NEAR_N * px_rcp_v(e.cmd));
         const float wm = e.w * m, wmm = e.w * m * m;
         const float M1_ex = seg_scan_add<L>(wm, h) - wm, M2_ex = seg_scan_add<L>(wmm, h) - wmm;
         float v[16];
@@ -868,7 +868,7 @@ __device__ __forceinline__ void shade_bwd_body(const FastParams& p, int cls, flo
         if (e.contrib) {
             const int gidx = e.gidx;
             const float alpha = e.alpha, T_prev = e.T_prev, w = e.w, G = e.G, cmd = e.cmd;
-            const float r1ma = px_rcp(1.0f - alpha);
+            const float r1ma = px_rcp_v(1.0f - alpha);
             const float cc[3] = {e.c.x, e.c.y, e.c.z}, Cc[3] = {Cx, Cy, Cz}, O[2] = {O0, O1};
             float dL_dalpha = 0.0f;
             float dL_dcolor[3];
@@ -894,7 +894,7 @@ __device__ __forceinline__ void shade_bwd_body(const FastParams& p, int cls, flo
             const float dL_dopac = dL_dalpha * G;   // straight-through cap (backward.cu:801-806)
 
             // compute_transmat_uv_backward (backward.cu:233-335), plane form t = m.(mu-o)/(m.d), m = t_u x t_v
-            const float isx = px_rcp(e.scale.x), isy = px_rcp(e.scale.y);
+            const float isx = px_rcp_v(e.scale.x), isy = px_rcp_v(e.scale.y);
             const float2 dL_duv = make_float2(dL_dG * -G * e.uv.x, dL_dG * -G * e.uv.y);
             const float3 xm = e.xyz - e.mu;
             float3 dR0 = (dL_duv.x * isx) * xm;
@@ -905,7 +905,7 @@ __device__ __forceinline__ void shade_bwd_body(const FastParams& p, int cls, flo
             const float3 dL_dxyz = (dL_duv.x * isx) * e.tu + (dL_duv.y * isy) * e.tv;
             const float dL_dd = dL_dD + dot(dL_dxyz, ray_d);
             const float3 mvec = cross(e.tu, e.tv);
-            const float iqd = px_rcp(dot(mvec, ray_d));
+            const float iqd = px_rcp_v(dot(mvec, ray_d));
             const float3 cvec = e.mu - ray_o;
             const float pn = dot(mvec, cvec);
             const float3 dt_dm = (cvec - (pn * iqd) * ray_d) * iqd;

@@ -14,6 +14,8 @@ import torch
 import torch.distributed as dist
 import torch.nn as nn
 
+from . import gradsink
+
 
 class FlatParameters:
     """Re-homes every parameter of `module` (and its gradient) into two contiguous fp32 buffers.
@@ -51,22 +53,41 @@ class FlatParameters:
             off += n
         self.total = total
 
+    def view_of(self, k: int, buf: torch.Tensor) -> torch.Tensor:
+        off, n = self.offsets[k]
+        return buf[off:off + n].view_as(self.params[k])
+
     def grad_is_view(self, k: int) -> bool:
         p, (off, _) = self.params[k], self.offsets[k]
         return p.grad is not None and p.grad.data_ptr() == self.flat_grad.data_ptr() + 4 * off
 
+    def register_sinks(self) -> None:
+        """Let the operators' backward kernels write these parameters' gradients straight into `flat_grad` (gradsink.py)."""
+        for k, p in enumerate(self.params):
+            gradsink.register(p, self.view_of(k, self.flat_grad))
+
+    def begin_backward(self) -> None:
+        """`.grad = None` so that autograd ADOPTS the first gradient tensor of each parameter instead of adding it to an
+        existing one — for a parameter with a sink that tensor is the flat-buffer slice the kernel already wrote."""
+        gradsink.begin_step()
+        for p in self.params:
+            p.grad = None
+
+    def home_grad(self, k: int) -> None:
+        """After backward: make sure parameter k's complete gradient sits in its flat-buffer slice and `.grad` views it."""
+        p = self.params[k]
+        if p.grad is not None and not self.grad_is_view(k):     # autograd built a separate tensor (no sink, or several contributions)
+            self.view_of(k, self.flat_grad).copy_(p.grad)       # ... which holds the COMPLETE gradient: overwrite, do not add
+        p.grad = self.view_of(k, self.flat_grad)
+
     def zero_grad(self):
         self.flat_grad.zero_()
-        for p, (off, n) in zip(self.params, self.offsets):   # autograd may have replaced the view; re-attach
-            if p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * off:
-                p.grad = self.flat_grad[off:off + n].view_as(p)
+        for k in range(len(self.params)):
+            self.params[k].grad = self.view_of(k, self.flat_grad)
 
     def collect_stray_grads(self, start: int = 0):
-        """If autograd swapped a .grad tensor instead of accumulating in place, fold it back into the flat buffer."""
-        for p, (off, n) in list(zip(self.params, self.offsets))[start:]:
-            if p.grad is not None and p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * off:
-                self.flat_grad[off:off + n].add_(p.grad.reshape(-1))
-                p.grad = self.flat_grad[off:off + n].view_as(p)
+        for k in range(start, len(self.params)):
+            self.home_grad(k)
 
 
 def init_process_group_from_env(backend: str | None = None) -> tuple[int, int, int]:
@@ -127,6 +148,7 @@ class ViewParallelTrainer:
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.flat = FlatParameters(renderer, pad=1024 * 8)
+        self.flat.register_sinks()
         self.average = average
         self.opt = None
         self.fused = self.fused_early = None
@@ -163,7 +185,9 @@ class ViewParallelTrainer:
             self._early_seen += 1
             if self._early_seen == self.flat.n_early_params and self._early_work is None:
                 first_early = len(self.flat.params) - self.flat.n_early_params
-                if all(self.flat.grad_is_view(j) for j in range(first_early, len(self.flat.params))):
+                for j in range(first_early, len(self.flat.params)):      # every early gradient is final here (post-accumulate)
+                    self.flat.home_grad(j)
+                if True:
                     e0, e1 = self.flat.early_range
                     # NCCL's stream picks up after everything queued on the compute stream so far (the tracer's backward) and
                     # runs concurrently with what is queued next (the rasterizer's backward)
@@ -176,20 +200,21 @@ class ViewParallelTrainer:
         self._early_seen, self._early_work = 0, None
         out = self.renderer(cam, target)
         loss = self.renderer.loss(out, target)
+        self.flat.begin_backward()
         loss.backward()
         scale = 1.0 / self.world if (self.world > 1 and self.average) else 1.0
         l0, l1 = self.flat.late_range
         e0, e1 = self.flat.early_range
         if self.world > 1:
             first_early = len(self.flat.params) - self.flat.n_early_params
-            if self._early_work is None:                 # hooks did not fire in place: exchange everything now
+            if self._early_work is None:                 # no early group / hooks disabled: exchange everything now
                 self.flat.collect_stray_grads()
                 if not self.shard:
                     dist.all_reduce(self.flat.flat_grad, op=dist.ReduceOp.SUM)
                 elif e1 > e0:
                     dist.all_reduce(self.flat.flat_grad[e0:e1], op=dist.ReduceOp.SUM)
             else:
-                self.flat.collect_stray_grads()          # late group only can be stray here; early views were checked in the hook
+                self.flat.collect_stray_grads(0)         # the early group was homed in the hook; homing it again is a no-op
                 if not self.shard:
                     dist.all_reduce(self.flat.flat_grad[l0:l1], op=dist.ReduceOp.SUM)
                 self._early_work.wait()

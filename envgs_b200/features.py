@@ -8,6 +8,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib
+from . import gradsink
 
 
 class _SHFeatures(torch.autograd.Function):
@@ -35,7 +36,7 @@ class _SHFeatures(torch.autograd.Function):
         dev = m.device
         g = grad_out.float().contiguous()
         d_means = torch.empty((P, 3), dtype=torch.float32, device=dev)
-        d_shs = torch.empty((P, M, 3), dtype=torch.float32, device=dev)
+        d_shs = gradsink.empty_or_sink(s, (P, M, 3), dtype=torch.float32, device=dev)   # 192 MB at 1 M surfels: written in place
         d_extra = torch.empty((P, E), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             _lib.check(L.envgs_sh_features_backward(P, D, M, E, _lib.ptr(m), _lib.ptr(s), _lib.ptr(c), _lib.ptr(g), _lib.ptr(d_means),

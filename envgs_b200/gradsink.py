@@ -1,0 +1,55 @@
+"""Gradient sinks: let the operators' backward kernels write parameter gradients straight into the trainer's flat gradient
+buffer ("backward kernels write straight into this buffer").
+
+Without a sink, every backward allocates a zero-filled tensor per gradient, the kernel fills it, and autograd's AccumulateGrad
+then adds it into the parameter's `.grad` (a view of the flat buffer): one extra read + read + write pass over ~300 MB per step
+plus the zero fills.  With a sink registered for a parameter, the backward wrapper asks `take(saved_tensor)` for its output
+buffer and gets the parameter's slice of the flat gradient buffer itself (the trainer keeps it zeroed between steps: the
+fused Adam pass clears what it consumed); the wrapper returns that very tensor as the gradient and, because the trainer leaves
+`param.grad = None` before `backward()`, AccumulateGrad adopts it without a copy.  A second gradient for the same parameter in
+the same step (e.g. the base means receive one from the rasterizer and one from the SH feature kernel) falls back to a fresh
+tensor and is accumulated by autograd as usual.
+"""
+from __future__ import annotations
+
+import torch
+
+_SINKS: dict = {}     # (device index, data_ptr of the parameter) -> [flat view, taken-this-step flag]
+
+
+def register(param: torch.Tensor, grad_view: torch.Tensor) -> None:
+    assert grad_view.numel() == param.numel() and grad_view.dtype == torch.float32
+    _SINKS[(param.device.index, param.data_ptr())] = [grad_view, False]
+
+
+def clear() -> None:
+    _SINKS.clear()
+
+
+def begin_step() -> None:
+    for v in _SINKS.values():
+        v[1] = False
+
+
+def take(saved: torch.Tensor, shape) -> torch.Tensor | None:
+    """The sink of the parameter `saved` aliases (autograd hands the backward a detached alias: same storage, same pointer), viewed
+    as `shape`; None if there is none or it was already handed out in this step."""
+    if not _SINKS:
+        return None
+    ent = _SINKS.get((saved.device.index, saved.data_ptr()))
+    if ent is None or ent[1] or ent[0].numel() != saved.numel():
+        return None
+    ent[1] = True
+    return ent[0].view(shape)
+
+
+def zeros_or_sink(saved: torch.Tensor, shape, **kw) -> torch.Tensor:
+    """Buffer for a gradient the kernel ACCUMULATES into (atomics / += on a zeroed buffer)."""
+    t = take(saved, shape)
+    return t if t is not None else torch.zeros(shape, **kw)
+
+
+def empty_or_sink(saved: torch.Tensor, shape, **kw) -> torch.Tensor:
+    """Buffer for a gradient the kernel overwrites completely."""
+    t = take(saved, shape)
+    return t if t is not None else torch.empty(shape, **kw)

@@ -12,6 +12,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from . import gradsink
 
 
 class GaussianRasterizationSettings(NamedTuple):
@@ -217,9 +218,12 @@ def make_module(C_channels: int):
                         else grad_depth.to(torch.float32).contiguous())
 
             z = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=device)
-            dL_dmeans3D, dL_dmeans2D, dL_dcolors = z(P, 3), z(P, 3), z(P, C_channels)
-            dL_dnormal, dL_dopacity, dL_dtransMat = z(P, 3), z(P, 1), z(P, 9)
-            dL_dsh, dL_dscales, dL_drotations = z(P, M, 3), z(P, 2), z(P, 4)
+            zs = lambda saved, *shape: gradsink.zeros_or_sink(saved, shape, dtype=torch.float32, device=device)   # flat-buffer slice if registered
+            dL_dmeans3D, dL_dmeans2D, dL_dcolors = zs(m3, P, 3), z(P, 3), z(P, C_channels)
+            dL_dnormal, dL_dopacity, dL_dtransMat = z(P, 3), zs(opa, P, 1), z(P, 9)
+            dL_dsh = zs(shc, P, M, 3) if M else z(P, M, 3)
+            dL_dscales = zs(sc, P, 2) if sc.numel() else z(P, 2)
+            dL_drotations = zs(rot, P, 4) if rot.numel() else z(P, 4)
 
             if P != 0:
                 vm, pm, cam = _f32c(s.viewmatrix, device), _f32c(s.projmatrix, device), _f32c(s.campos, device)

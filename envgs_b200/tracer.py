@@ -14,6 +14,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from . import gradsink
 
 NUM_CHANNELS = 3
 AUX_CHANNELS = 2
@@ -245,9 +246,12 @@ class _TraceSurfels(torch.autograd.Function):
         g_norm, g_dist, g_aux = up(grad_out_norm, (H, W, 3)), up(grad_out_dist, (H, W, 1)), up(grad_out_aux, (H, W, AUX_CHANNELS))
 
         dL_dray_o, dL_dray_d = torch.empty((H, W, 3), **f), torch.empty((H, W, 3), **f)
-        dL_dmeans3D, dL_dshs, dL_dcolors = torch.zeros((P, 3), **f), torch.zeros((P, M, 3), **f), torch.zeros((P, NUM_CHANNELS), **f)
-        dL_dothers, dL_dopacities = torch.zeros((P, AUX_CHANNELS), **f), torch.zeros((P, 1), **f)
-        dL_dscales, dL_drotations, dL_dtransMat = torch.zeros((P, 2), **f), torch.zeros((P, 4), **f), torch.zeros((P, 9), **f)
+        zs = lambda saved, *shape: gradsink.zeros_or_sink(saved, shape, **f)     # the trainer's flat-buffer slice if registered
+        dL_dmeans3D = zs(m3, P, 3)
+        dL_dshs = zs(sh, P, M, 3) if M else torch.zeros((P, M, 3), **f)
+        dL_dcolors = torch.zeros((P, NUM_CHANNELS), **f)
+        dL_dothers, dL_dopacities = torch.zeros((P, AUX_CHANNELS), **f), zs(opa, P, 1)
+        dL_dscales, dL_drotations, dL_dtransMat = zs(sc, P, 2), zs(rot, P, 4), torch.zeros((P, 9), **f)
 
         vm, pm, cam = _f32c(s.viewmatrix, device), _f32c(s.projmatrix, device), _f32c(s.campos, device)
         args = _trace_args(P, H, W, s, False, ctx.start_from_first, ro, rd, ctx.bg, m3, sh, col, oth, opa, sc, rot, vm, pm, cam)

@@ -1,2 +1,8 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 8 --steps 30 --warmup 5 --no-profile > gpurun_out/scale_r2_v5_n8.json 2> gpurun_out/scale_r2_v5_n8.err; tail -c 900 gpurun_out/scale_r2_v5_n8.json | head -c 900; echo
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus 8 --workload config5 --steps 8 --warmup 3 --no-profile > gpurun_out/scale_r2_config5_n8.json 2> gpurun_out/scale_r2_config5_n8.err; head -c 700 gpurun_out/scale_r2_config5_n8.json; tail -2 gpurun_out/scale_r2_config5_n8.err
+python -m pytest tests -m gpu -q --tb=short -x 2>&1 | tail -4
+python bench.py --steps 32 --warmup 5 --no-cpu-baseline --no-ref-gpu > gpurun_out/bench_r2_v6.json 2> gpurun_out/bench_r2_v6.err; python - <<'PY'
+import json
+d=json.loads(open("gpurun_out/bench_r2_v6.json").read().strip().splitlines()[-1])
+print(d["value"], d["ms_per_step"], d["e2e"]["ms_per_step"], d["gpu_launches"]); print({k:v for k,v in d["kernels_ms"].items() if v>0.15})
+PY
+tail -3 gpurun_out/bench_r2_v6.err
+python tools/prof_step.py config3 3 --stats 2>&1 | grep nodes
