@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: do not start the environment group's all-reduce from the gradient hook")
     ap.add_argument("--no-shard", action="store_true", help="N > 1: all-reduce + full-size Adam instead of reduce-scatter / sharded Adam / all-gather")
+    ap.add_argument("--no-factored-sh", action="store_true", help="N > 1: exchange the base SH gradient itself instead of its rank-one factors")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip the in-process timing of the reference GPU operators")
     ap.add_argument("--reference-device", default="auto", choices=["auto", "cpu"],
                     help="--impl reference: 'auto' runs the real reference on the GPU when it can (else the CPU port); 'cpu' forces the CPU port")
@@ -312,7 +313,7 @@ def main():
         env.specular.fill_(0.5)                           # every second-segment ray continues unless its first segment saw nothing
     renderer = EnvGSRenderer(base, env, device=dev, max_trace_depth=TRACE_DEPTH.get(args.workload, 0))
     trainer = ViewParallelTrainer(renderer, lr=1e-6, average=True, optimizer=True, overlap=not args.no_overlap,
-                                  shard_optimizer=not args.no_shard)
+                                  shard_optimizer=not args.no_shard, factored_sh=not args.no_factored_sh)
     n_views = 138                                         # sedan-sized view list
     cams_cpu = scene.ring_cameras(n_views, H, W, seed=2)
     gt = torch.Generator().manual_seed(3)

@@ -88,7 +88,7 @@ EXPORTS = [
     "envgs_last_error", "envgs_version", "envgs_raster_forward", "envgs_raster_backward", "envgs_mark_visible",
     "envgs_raster_geom_bytes", "envgs_raster_img_bytes", "envgs_raster_binning_bytes", "envgs_tracer_create",
     "envgs_tracer_destroy", "envgs_tracer_build", "envgs_tracer_bvh_bytes", "envgs_trace_forward",
-    "envgs_trace_backward", "envgs_launch_count", "envgs_profile_enable", "envgs_profile_report", "envgs_debug_trace_stats", "envgs_trace_cache_bytes", "envgs_trace_cache_bytes2", "envgs_sh_features_forward", "envgs_sh_features_backward",
+    "envgs_trace_backward", "envgs_launch_count", "envgs_profile_enable", "envgs_profile_report", "envgs_debug_trace_stats", "envgs_trace_cache_bytes", "envgs_trace_cache_bytes2", "envgs_sh_features_forward", "envgs_sh_features_backward", "envgs_sh_features_backward_factored", "envgs_sh_adam_factored",
     "envgs_glue_reflect_forward", "envgs_glue_reflect_backward", "envgs_glue_blend_loss_forward", "envgs_glue_blend_loss_backward",
     "envgs_adam_step", "envgs_glue_quad_vertices",
     "envgs_densify_stats", "envgs_densify_plan_scratch_bytes", "envgs_densify_plan", "envgs_densify_apply", "envgs_rows_gather",
@@ -144,6 +144,10 @@ def lib() -> C.CDLL:
     L.envgs_sh_features_forward.argtypes = [C.c_int32] * 4 + [C.c_void_p] * 6
     L.envgs_sh_features_backward.restype = C.c_int
     L.envgs_sh_features_backward.argtypes = [C.c_int32] * 4 + [C.c_void_p] * 8
+    L.envgs_sh_features_backward_factored.restype = C.c_int
+    L.envgs_sh_features_backward_factored.argtypes = [C.c_int32] * 4 + [C.c_void_p] * 8
+    L.envgs_sh_adam_factored.restype = C.c_int
+    L.envgs_sh_adam_factored.argtypes = [C.c_int32] * 4 + [C.c_void_p] * 6 + [C.c_int32] + [C.c_float] * 5 + [C.c_void_p]
     L.envgs_glue_reflect_forward.restype = C.c_int
     L.envgs_glue_reflect_forward.argtypes = [C.POINTER(GlueCamera)] + [C.c_void_p] * 4
     L.envgs_glue_reflect_backward.restype = C.c_int

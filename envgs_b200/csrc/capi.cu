@@ -60,7 +60,8 @@ int glue_blend_loss_backward(const envgs_glue_camera& cam, const float* image, c
 int adam_step_impl(size_t n, float* p, float* g, float* m, float* v, int step, float lr, float b1, float b2, float eps, float grad_scale,
                    int zero_grad, cudaStream_t stream);
 int sh_features_forward_impl(int P, int D, int M, int E, const float* means, const float* shs, const float* extra, const float* campos, float* out, cudaStream_t stream);
-int sh_features_backward_impl(int P, int D, int M, int E, const float* means, const float* shs, const float* campos, const float* dL_dout, float* dL_dmeans, float* dL_dshs, float* dL_dextra, cudaStream_t stream);
+int sh_features_backward_impl(int P, int D, int M, int E, const float* means, const float* shs, const float* campos, const float* dL_dout, float* dL_dmeans, float* dL_dshs, float* dL_dextra, float* dL_dfactor, cudaStream_t stream);
+int sh_adam_factored_impl(int P, int D, int M, int N, const float* means, const float* campos_all, const float* factors_all, float* shs, float* exp_avg, float* exp_avg_sq, int step, float lr, float b1, float b2, float eps, float grad_scale, cudaStream_t stream);
 bool trace_fast_eligible(const envgs_trace_args& a, const void* cache);
 struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; };
 int trace_forward_fast(Lbvh& bvh, unsigned int* counter, unsigned long long* stats, const envgs_trace_args& a, const envgs_trace_out& o, void* cache, cudaStream_t stream, const SideStream& side);
@@ -263,7 +264,26 @@ int envgs_sh_features_backward(int32_t P, int32_t D, int32_t M, int32_t E, const
     int rc = check_features(P, D, M, E);
     if (rc != ENVGS_OK) return rc;
     if (P > 0 && (!means3D || !shs || !campos || !dL_dout || !dL_dmeans3D || !dL_dshs || (E > 0 && !dL_dextra))) { set_error("sh_features pointer is NULL"); return ENVGS_ERR_INVALID; }
-    return sh_features_backward_impl(P, D, M, E, means3D, shs, campos, dL_dout, dL_dmeans3D, dL_dshs, dL_dextra, (cudaStream_t)stream);
+    return sh_features_backward_impl(P, D, M, E, means3D, shs, campos, dL_dout, dL_dmeans3D, dL_dshs, dL_dextra, nullptr, (cudaStream_t)stream);
+}
+
+int envgs_sh_features_backward_factored(int32_t P, int32_t D, int32_t M, int32_t E, const float* means3D, const float* shs, const float* campos,
+                                        const float* dL_dout, float* dL_dmeans3D, float* dL_dfactor, float* dL_dextra, void* stream) {
+    int rc = check_features(P, D, M, E);
+    if (rc != ENVGS_OK) return rc;
+    if (P > 0 && (!means3D || !shs || !campos || !dL_dout || !dL_dmeans3D || !dL_dfactor || (E > 0 && !dL_dextra))) { set_error("sh_features pointer is NULL"); return ENVGS_ERR_INVALID; }
+    return sh_features_backward_impl(P, D, M, E, means3D, shs, campos, dL_dout, dL_dmeans3D, nullptr, dL_dextra, dL_dfactor, (cudaStream_t)stream);
+}
+
+int envgs_sh_adam_factored(int32_t P, int32_t D, int32_t M, int32_t n_views, const float* means3D, const float* campos_all,
+                           const float* factors_all, float* shs, float* exp_avg, float* exp_avg_sq, int32_t step, float lr, float beta1,
+                           float beta2, float eps, float grad_scale, void* stream) {
+    int rc = check_features(P, D, M, 0);
+    if (rc != ENVGS_OK) return rc;
+    if (n_views < 1 || step < 1) { set_error("bad sh_adam_factored arguments n_views=%d step=%d", n_views, step); return ENVGS_ERR_INVALID; }
+    if (P > 0 && (!means3D || !campos_all || !factors_all || !shs || !exp_avg || !exp_avg_sq)) { set_error("sh_adam_factored pointer is NULL"); return ENVGS_ERR_INVALID; }
+    return sh_adam_factored_impl(P, D, M, n_views, means3D, campos_all, factors_all, shs, exp_avg, exp_avg_sq, step, lr, beta1, beta2, eps,
+                                 grad_scale, (cudaStream_t)stream);
 }
 
 int envgs_debug_trace_stats(envgs_tracer* h, int32_t enable, uint64_t out[8]) {

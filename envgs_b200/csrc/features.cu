@@ -101,7 +101,8 @@ __global__ void __launch_bounds__(SHF_THREADS) sh_features_fwd_kernel(int P, int
 __global__ void __launch_bounds__(SHF_THREADS) sh_features_bwd_kernel(int P, int D, int M, int E, const float* __restrict__ means,
                                                                       const float* __restrict__ shs, const float* __restrict__ campos,
                                                                       const float* __restrict__ dL_dout, float* __restrict__ dL_dmeans,
-                                                                      float* __restrict__ dL_dshs, float* __restrict__ dL_dextra) {
+                                                                      float* __restrict__ dL_dshs, float* __restrict__ dL_dextra,
+                                                                      float* __restrict__ dL_dfactor) {
     __shared__ float s_tile[(SHF_THREADS / 32) * 32 * (SHF_MAXROW + 1)];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int warp_first = blockIdx.x * SHF_THREADS + warp * 32;
@@ -133,12 +134,81 @@ __global__ void __launch_bounds__(SHF_THREADS) sh_features_bwd_kernel(int P, int
             }
             sh[3 * k] = bk * dRGB.x; sh[3 * k + 1] = bk * dRGB.y; sh[3 * k + 2] = bk * dRGB.z;
         }
+        if (dL_dfactor) { dL_dfactor[3 * (size_t)i] = dRGB.x; dL_dfactor[3 * (size_t)i + 1] = dRGB.y; dL_dfactor[3 * (size_t)i + 2] = dRGB.z; }
         const float3 dm = dnormvdv(dir_orig, dL_ddir);
         dL_dmeans[3 * (size_t)i] = dm.x; dL_dmeans[3 * (size_t)i + 1] = dm.y; dL_dmeans[3 * (size_t)i + 2] = dm.z;
         for (int e = 0; e < E; e++) dL_dextra[(size_t)i * E + e] = g[3 + e];
     }
     __syncwarp();
-    shf_tile_store(dL_dshs, P, row, warp_first, lane, tile);
+    if (dL_dshs) shf_tile_store(dL_dshs, P, row, warp_first, lane, tile);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Factored exchange of the SH gradient (view-parallel training)
+// ------------------------------------------------------------------------------------------------------
+// One view's gradient of a surfel's (M,3) SH coefficients is RANK ONE: basis(dir_i) (M values, a function of the surfel's
+// position and that view's camera centre) times the clamp-masked colour gradient (3 values).  Summing it over N ranks with an
+// all-reduce moves 4*M*3 = 192 B per surfel both ways; all-GATHERING the 12-byte factors and rebuilding the sum locally moves
+// 12*N bytes one way — 4x less at N = 8 for the 80 % of the base set's gradient bytes that are SH.  This kernel is the
+// receiving end fused with the optimizer: per surfel, sum_r basis(normalize(mean_i - campos_r)) (x) factor_r,i in fixed rank
+// order (every rank computes bit-identical sums, so the replicas stay in sync), then the Adam update of the 3M coefficients
+// (same arithmetic as adam_step_kernel).  Coefficients and moments move through padded shared-memory tiles like above.
+constexpr int SHA_THREADS = 64;
+__global__ void __launch_bounds__(SHA_THREADS) sh_adam_factored_kernel(int P, int D, int M, int N, const float* __restrict__ means,
+                                                                        const float* __restrict__ campos_all, const float* __restrict__ factors_all,
+                                                                        float* __restrict__ shs, float* __restrict__ exp_avg,
+                                                                        float* __restrict__ exp_avg_sq, float lr_over_bc1, float inv_sqrt_bc2,
+                                                                        float b1, float b2, float eps, float grad_scale) {
+    __shared__ float s_tile[3][(SHA_THREADS / 32) * 32 * (SHF_MAXROW + 1)];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int warp_first = blockIdx.x * SHA_THREADS + warp * 32;
+    if (warp_first >= P) return;
+    const int row = M * 3;
+    float* tp = s_tile[0] + warp * 32 * (SHF_MAXROW + 1);
+    float* tm = s_tile[1] + warp * 32 * (SHF_MAXROW + 1);
+    float* tv = s_tile[2] + warp * 32 * (SHF_MAXROW + 1);
+    shf_tile_load(shs, P, row, warp_first, lane, tp);
+    shf_tile_load(exp_avg, P, row, warp_first, lane, tm);
+    shf_tile_load(exp_avg_sq, P, row, warp_first, lane, tv);
+    __syncwarp();
+    const int i = warp_first + lane;
+    if (i < P) {
+        const float3 mean = ld3(means, i);
+        const int nb = (D + 1) * (D + 1);
+        float g[SHF_MAXROW];
+#pragma unroll
+        for (int q = 0; q < SHF_MAXROW; q++) g[q] = 0.0f;
+        for (int r = 0; r < N; r++) {
+            const float3 dir_orig = mean - f3(campos_all[3 * r], campos_all[3 * r + 1], campos_all[3 * r + 2]);
+            const float3 dir = dir_orig / fmaxf(length3(dir_orig), 1e-12f);
+            float b[16];
+            sh_basis(D, dir, b);
+            const float* f = factors_all + ((size_t)r * P + i) * 3;
+            const float fx = f[0], fy = f[1], fz = f[2];
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const float bk = k < nb ? b[k] : 0.0f;
+                g[3 * k] += bk * fx; g[3 * k + 1] += bk * fy; g[3 * k + 2] += bk * fz;
+            }
+        }
+        float* pp = tp + lane * (row + 1);
+        float* mm = tm + lane * (row + 1);
+        float* vv = tv + lane * (row + 1);
+#pragma unroll
+        for (int q = 0; q < SHF_MAXROW; q++) {
+            if (q < row) {
+                const float gg = g[q] * grad_scale;
+                const float m1 = b1 * mm[q] + (1.0f - b1) * gg;
+                const float v1 = b2 * vv[q] + (1.0f - b2) * gg * gg;
+                mm[q] = m1; vv[q] = v1;
+                pp[q] -= lr_over_bc1 * m1 / (sqrtf(v1) * inv_sqrt_bc2 + eps);
+            }
+        }
+    }
+    __syncwarp();
+    shf_tile_store(shs, P, row, warp_first, lane, tp);
+    shf_tile_store(exp_avg, P, row, warp_first, lane, tm);
+    shf_tile_store(exp_avg_sq, P, row, warp_first, lane, tv);
 }
 
 int sh_features_forward_impl(int P, int D, int M, int E, const float* means, const float* shs, const float* extra, const float* campos,
@@ -150,11 +220,25 @@ int sh_features_forward_impl(int P, int D, int M, int E, const float* means, con
     return ENVGS_OK;
 }
 int sh_features_backward_impl(int P, int D, int M, int E, const float* means, const float* shs, const float* campos, const float* dL_dout,
-                              float* dL_dmeans, float* dL_dshs, float* dL_dextra, cudaStream_t stream) {
+                              float* dL_dmeans, float* dL_dshs, float* dL_dextra, float* dL_dfactor, cudaStream_t stream) {
     if (P <= 0) return ENVGS_OK;
     ENVGS_TIMED("sh_features_bwd", stream);
-    sh_features_bwd_kernel<<<(P + SHF_THREADS - 1) / SHF_THREADS, SHF_THREADS, 0, stream>>>(P, D, M, E, means, shs, campos, dL_dout, dL_dmeans, dL_dshs, dL_dextra);
+    sh_features_bwd_kernel<<<(P + SHF_THREADS - 1) / SHF_THREADS, SHF_THREADS, 0, stream>>>(P, D, M, E, means, shs, campos, dL_dout, dL_dmeans, dL_dshs,
+                                                                                            dL_dextra, dL_dfactor);
     ENVGS_LAUNCH_CHECK("sh_features_bwd", false, stream);
+    return ENVGS_OK;
+}
+
+int sh_adam_factored_impl(int P, int D, int M, int N, const float* means, const float* campos_all, const float* factors_all, float* shs,
+                          float* exp_avg, float* exp_avg_sq, int step, float lr, float b1, float b2, float eps, float grad_scale,
+                          cudaStream_t stream) {
+    if (P <= 0) return ENVGS_OK;
+    ENVGS_TIMED("sh_adam_factored", stream);
+    const double bc1 = 1.0 - pow((double)b1, (double)step), bc2 = 1.0 - pow((double)b2, (double)step);
+    sh_adam_factored_kernel<<<(P + SHA_THREADS - 1) / SHA_THREADS, SHA_THREADS, 0, stream>>>(P, D, M, N, means, campos_all, factors_all, shs, exp_avg,
+                                                                                             exp_avg_sq, (float)(lr / bc1), (float)(1.0 / sqrt(bc2)),
+                                                                                             b1, b2, eps, grad_scale);
+    ENVGS_LAUNCH_CHECK("sh_adam_factored", false, stream);
     return ENVGS_OK;
 }
 

@@ -25,17 +25,20 @@ class FlatParameters:
     rasterizer's), so their exchange can start while the rest is still being computed.  Both groups are padded to a multiple
     of `pad` floats so that a group can be reduce-scattered across any world size that divides `pad`."""
 
-    def __init__(self, module: nn.Module, early_prefixes: tuple = ("env_",), pad: int = 1024):
+    def __init__(self, module: nn.Module, early_prefixes: tuple = ("env_",), pad: int = 1024, factored_names: tuple = ()):
         named = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
-        late = [(n, p) for n, p in named if not n.startswith(tuple(early_prefixes))]
-        early = [(n, p) for n, p in named if n.startswith(tuple(early_prefixes))]
-        self.names = [n for n, _ in late + early]
-        self.params = [p for _, p in late + early]
+        fact = [(n, p) for n, p in named if n in factored_names]
+        late = [(n, p) for n, p in named if not n.startswith(tuple(early_prefixes)) and n not in factored_names]
+        early = [(n, p) for n, p in named if n.startswith(tuple(early_prefixes)) and n not in factored_names]
+        self.names = [n for n, _ in late + fact + early]
+        self.params = [p for _, p in late + fact + early]
         rnd = lambda x: (x + pad - 1) // pad * pad
-        n_late, n_early = sum(p.numel() for _, p in late), sum(p.numel() for _, p in early)
+        n_late, n_fact, n_early = (sum(p.numel() for _, p in grp) for grp in (late, fact, early))
         self.late_range = (0, rnd(n_late))
-        self.early_range = (rnd(n_late), rnd(n_late) + rnd(n_early))
+        self.factored_range = (rnd(n_late), rnd(n_late) + rnd(n_fact))      # the base SH coefficients when their exchange is factored
+        self.early_range = (self.factored_range[1], self.factored_range[1] + rnd(n_early))
         self.n_early_params = len(early)
+        self._group_starts = {len(late): self.factored_range[0], len(late) + len(fact): self.early_range[0]}
         total = self.early_range[1]
         dev = self.params[0].device
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
@@ -43,8 +46,7 @@ class FlatParameters:
         self.offsets = []
         off = 0
         for k, p in enumerate(self.params):
-            if k == len(late):
-                off = self.early_range[0]
+            off = self._group_starts.get(k, off)
             n = p.numel()
             self.flat[off:off + n].copy_(p.data.reshape(-1))
             p.data = self.flat[off:off + n].view_as(p)
@@ -143,11 +145,16 @@ class ViewParallelTrainer:
     The gradient average (1/N) is folded into the fused Adam kernel."""
 
     def __init__(self, renderer: nn.Module, lr: float = 1e-4, average: bool = True, optimizer: bool = True, overlap: bool = True,
-                 shard_optimizer: bool = True):
+                 shard_optimizer: bool = True, factored_sh: bool = True):
         self.renderer = renderer
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.rank = dist.get_rank() if dist.is_initialized() else 0
-        self.flat = FlatParameters(renderer, pad=1024 * 8)
+        cuda0 = next(renderer.parameters()).is_cuda
+        # Factored exchange of the base SH gradient (features.cu, sh_adam_factored_kernel): needs the fused SH feature op
+        # (it produces the rank-one factor), NCCL and an optimizer to fuse the rebuild into.
+        self.factored = bool(factored_sh and optimizer and cuda0 and self.world > 1 and dist.get_backend() == "nccl"
+                             and getattr(renderer, "fused_features", False) and hasattr(renderer, "shs"))
+        self.flat = FlatParameters(renderer, pad=1024 * 8, factored_names=("shs",) if self.factored else ())
         self.flat.register_sinks()
         self.average = average
         self.opt = None
@@ -161,12 +168,27 @@ class ViewParallelTrainer:
                       and (self.flat.late_range[1] - self.flat.late_range[0]) % self.world == 0)
         l0, l1 = self.flat.late_range
         e0, e1 = self.flat.early_range
+        self.fused_sh = None
+        if self.factored:
+            f0, f1 = self.flat.factored_range
+            dev = self.flat.flat.device
+            shs = renderer.shs
+            P, M = shs.shape[0], shs.shape[1]
+            self._factor_local = torch.zeros(P, 3, dtype=torch.float32, device=dev)
+            self._factors_all = torch.zeros(self.world, P, 3, dtype=torch.float32, device=dev)
+            self._campos_local = torch.zeros(3, dtype=torch.float32, device=dev)
+            self._campos_all = torch.zeros(self.world, 3, dtype=torch.float32, device=dev)
+            self.fused_sh = FlatAdam(self.flat.flat[f0:f1], self.flat.flat_grad[f0:f1], lr=lr)   # owns the SH moments and step count
+            gradsink.register_factor(shs, self._factor_local, self._campos_local)
         if optimizer and cuda:
             if self.shard:
                 n = (l1 - l0) // self.world
                 self._shard_slice = slice(l0 + self.rank * n, l0 + (self.rank + 1) * n)
                 self._grad_shard = torch.zeros(n, dtype=torch.float32, device=self.flat.flat.device)
                 self.fused = FlatAdam(self.flat.flat[self._shard_slice], self._grad_shard, lr=lr)
+                self.fused_early = FlatAdam(self.flat.flat[e0:e1], self.flat.flat_grad[e0:e1], lr=lr) if e1 > e0 else None
+            elif self.factored:
+                self.fused = FlatAdam(self.flat.flat[l0:l1], self.flat.flat_grad[l0:l1], lr=lr)
                 self.fused_early = FlatAdam(self.flat.flat[e0:e1], self.flat.flat_grad[e0:e1], lr=lr) if e1 > e0 else None
             else:
                 self.fused = FlatAdam(self.flat.flat, self.flat.flat_grad, lr=lr)
@@ -205,24 +227,43 @@ class ViewParallelTrainer:
         scale = 1.0 / self.world if (self.world > 1 and self.average) else 1.0
         l0, l1 = self.flat.late_range
         e0, e1 = self.flat.early_range
+        f0, f1 = self.flat.factored_range
+        sh_factored = False
         if self.world > 1:
-            first_early = len(self.flat.params) - self.flat.n_early_params
-            if self._early_work is None:                 # no early group / hooks disabled: exchange everything now
-                self.flat.collect_stray_grads()
-                if not self.shard:
-                    dist.all_reduce(self.flat.flat_grad, op=dist.ReduceOp.SUM)
-                elif e1 > e0:
-                    dist.all_reduce(self.flat.flat_grad[e0:e1], op=dist.ReduceOp.SUM)
-            else:
-                self.flat.collect_stray_grads(0)         # the early group was homed in the hook; homing it again is a no-op
-                if not self.shard:
-                    dist.all_reduce(self.flat.flat_grad[l0:l1], op=dist.ReduceOp.SUM)
-                self._early_work.wait()
+            self.flat.collect_stray_grads(0)             # every gradient home in the flat buffer (early group: no-op after the hook)
+            works = []
+            if self.factored:
+                sh_factored = gradsink.factor_written(self.renderer.shs)
+                if sh_factored:                          # 12 B per surfel and rank instead of 192 B both ways
+                    works.append(dist.all_gather_into_tensor(self._factors_all, self._factor_local, async_op=True))
+                    works.append(dist.all_gather_into_tensor(self._campos_all, self._campos_local, async_op=True))
+                else:                                    # the SH gradient arrived the ordinary way (no fused feature op in this graph)
+                    works.append(dist.all_reduce(self.flat.flat_grad[f0:f1], op=dist.ReduceOp.SUM, async_op=True))
+            if self._early_work is None and e1 > e0:     # no hook launch (overlap off): exchange the early group now
+                works.append(dist.all_reduce(self.flat.flat_grad[e0:e1], op=dist.ReduceOp.SUM, async_op=True))
             if self.shard:
-                dist.reduce_scatter_tensor(self._grad_shard, self.flat.flat_grad[l0:l1], op=dist.ReduceOp.SUM)
+                works.append(dist.reduce_scatter_tensor(self._grad_shard, self.flat.flat_grad[l0:l1], op=dist.ReduceOp.SUM, async_op=True))
+            elif l1 > l0:
+                works.append(dist.all_reduce(self.flat.flat_grad[l0:l1], op=dist.ReduceOp.SUM, async_op=True))
+            for w in works:
+                w.wait()
+            if self._early_work is not None:
+                self._early_work.wait()
         else:
             self.flat.collect_stray_grads()
         if self.fused is not None:
+            if self.fused_sh is not None:                # before the positions move: the basis is a function of (mean - campos)
+                if sh_factored:
+                    from . import _lib
+                    shs, a = self.renderer.shs, self.fused_sh
+                    a.t += 1
+                    with torch.cuda.device(shs.device):
+                        _lib.check(_lib.lib().envgs_sh_adam_factored(
+                            shs.shape[0], 3, shs.shape[1], self.world, _lib.ptr(self.renderer.means), _lib.ptr(self._campos_all),
+                            _lib.ptr(self._factors_all), _lib.ptr(self.flat.flat[f0:f1]), _lib.ptr(a.exp_avg), _lib.ptr(a.exp_avg_sq), a.t, a.lr,
+                            a.betas[0], a.betas[1], a.eps, scale, torch.cuda.current_stream(shs.device).cuda_stream), "envgs_sh_adam_factored")
+                else:
+                    self.fused_sh.step(grad_scale=scale, zero_grad=True)
             if self.shard:
                 self.fused.step(grad_scale=scale, zero_grad=False)
                 if self.fused_early is not None:
@@ -231,6 +272,8 @@ class ViewParallelTrainer:
                 self.flat.flat_grad[l0:l1].zero_()
             else:
                 self.fused.step(grad_scale=scale, zero_grad=True)
+                if self.fused_early is not None and self.factored:
+                    self.fused_early.step(grad_scale=scale, zero_grad=True)
             self._grad_is_zero = True
         else:
             if scale != 1.0:

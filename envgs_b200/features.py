@@ -36,8 +36,19 @@ class _SHFeatures(torch.autograd.Function):
         dev = m.device
         g = grad_out.float().contiguous()
         d_means = torch.empty((P, 3), dtype=torch.float32, device=dev)
-        d_shs = gradsink.empty_or_sink(s, (P, M, 3), dtype=torch.float32, device=dev)   # 192 MB at 1 M surfels: written in place
         d_extra = torch.empty((P, E), dtype=torch.float32, device=dev)
+        fac = gradsink.take_factor(s)
+        if fac is not None:
+            # view-parallel trainer: hand over the rank-one factor (P,3) of this view's SH gradient and the camera centre instead
+            # of materialising the (P,M,3) gradient; the trainer all-gathers the factors and envgs_sh_adam_factored rebuilds the sum
+            fbuf, cbuf = fac
+            cbuf.copy_(c.reshape(-1)[:3])
+            with torch.cuda.device(dev):
+                _lib.check(L.envgs_sh_features_backward_factored(P, D, M, E, _lib.ptr(m), _lib.ptr(s), _lib.ptr(c), _lib.ptr(g), _lib.ptr(d_means),
+                                                                 _lib.ptr(fbuf), _lib.ptr(d_extra), torch.cuda.current_stream(dev).cuda_stream),
+                           "envgs_sh_features_backward_factored")
+            return d_means, None, d_extra, None, None
+        d_shs = gradsink.empty_or_sink(s, (P, M, 3), dtype=torch.float32, device=dev)   # 192 MB at 1 M surfels: written in place
         with torch.cuda.device(dev):
             _lib.check(L.envgs_sh_features_backward(P, D, M, E, _lib.ptr(m), _lib.ptr(s), _lib.ptr(c), _lib.ptr(g), _lib.ptr(d_means),
                                                     _lib.ptr(d_shs), _lib.ptr(d_extra), torch.cuda.current_stream(dev).cuda_stream),

@@ -24,11 +24,13 @@ def register(param: torch.Tensor, grad_view: torch.Tensor) -> None:
 
 def clear() -> None:
     _SINKS.clear()
+    _FACTORS.clear()
 
 
 def begin_step() -> None:
     for v in _SINKS.values():
         v[1] = False
+    begin_step_factors()
 
 
 def take(saved: torch.Tensor, shape) -> torch.Tensor | None:
@@ -53,3 +55,31 @@ def empty_or_sink(saved: torch.Tensor, shape, **kw) -> torch.Tensor:
     """Buffer for a gradient the kernel overwrites completely."""
     t = take(saved, shape)
     return t if t is not None else torch.empty(shape, **kw)
+
+
+# ---- factored SH gradient (view-parallel training, dist.py) -----------------------------------------------------------------
+_FACTORS: dict = {}   # (device index, data_ptr of the SH parameter) -> [(P,3) buffer, camera-centre slot (3,), written-this-step flag]
+
+
+def register_factor(sh_param: torch.Tensor, factor_buf: torch.Tensor, campos_buf: torch.Tensor) -> None:
+    _FACTORS[(sh_param.device.index, sh_param.data_ptr())] = [factor_buf, campos_buf, False]
+
+
+def take_factor(saved_shs: torch.Tensor):
+    """If the trainer asked for the rank-one factor of this SH parameter's gradient instead of the gradient itself: the (P,3)
+    buffer to write it into and the slot that receives this view's camera centre; else None."""
+    ent = _FACTORS.get((saved_shs.device.index, saved_shs.data_ptr())) if _FACTORS else None
+    if ent is None or ent[2]:
+        return None
+    ent[2] = True
+    return ent[0], ent[1]
+
+
+def begin_step_factors() -> None:
+    for v in _FACTORS.values():
+        v[2] = False
+
+
+def factor_written(sh_param: torch.Tensor) -> bool:
+    ent = _FACTORS.get((sh_param.device.index, sh_param.data_ptr()))
+    return bool(ent and ent[2])

@@ -261,6 +261,18 @@ int envgs_sh_features_backward(int32_t P, int32_t sh_degree, int32_t sh_coeffs, 
                                const float* campos, const float* dL_dout, float* dL_dmeans3D, float* dL_dshs, float* dL_dextra,
                                void* stream);
 
+/* View-parallel training: one view's SH gradient is rank one — basis(normalize(mean - campos)) (sh_coeffs values) times the
+ * clamp-masked colour gradient (3 values).  `_factored` writes only that (P,3) factor instead of the (P,sh_coeffs,3) gradient;
+ * envgs_sh_adam_factored rebuilds sum over n_views of basis (x) factor from the all-gathered factors (n_views,P,3) and camera
+ * centres (n_views,3) in fixed view order and applies the Adam update (arithmetic of envgs_adam_step) to the coefficients.
+ * `means3D` must be the positions the forward pass saw (call it before the positions are updated). */
+int envgs_sh_features_backward_factored(int32_t P, int32_t sh_degree, int32_t sh_coeffs, int32_t E, const float* means3D, const float* shs,
+                                        const float* campos, const float* dL_dout, float* dL_dmeans3D, float* dL_dfactor, float* dL_dextra,
+                                        void* stream);
+int envgs_sh_adam_factored(int32_t P, int32_t sh_degree, int32_t sh_coeffs, int32_t n_views, const float* means3D, const float* campos_all,
+                           const float* factors_all, float* shs, float* exp_avg, float* exp_avg_sq, int32_t step, float lr, float beta1,
+                           float beta2, float eps, float grad_scale, void* stream);
+
 /* Per-pixel glue between the two operators, fused (reference: ~150 eager PyTorch launches per view —
  * gaussian2d_utils.py:1117-1153 + :1158-1206, ray_utils.py:24-78, envgs_sampler.py:420-431 + :474, plus the loss). */
 typedef struct envgs_glue_camera {

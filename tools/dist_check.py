@@ -21,7 +21,7 @@ tr = ViewParallelTrainer(r, lr=1e-3)
 for step in range(2):
     tr.step(cams[step * world + rank], target)
 torch.cuda.synchronize()
-mine = tr.flat.flat.clone()
+mine = {n: p.detach().clone() for n, p in r.named_parameters()}
 if rank == 0:
     r2 = EnvGSRenderer(base, env, device=dev)
     fp = FlatParameters(r2, pad=1024 * 8)
@@ -34,9 +34,15 @@ if rank == 0:
         fp.collect_stray_grads()
         adam.step(grad_scale=1.0 / world, zero_grad=True)
     torch.cuda.synchronize()
-    d = (mine - fp.flat).abs()
-    upd = (fp.flat - FlatParameters(EnvGSRenderer(base, env, device=dev), pad=1024 * 8).flat).abs()
-    print(f"world {world}: shard={tr.shard} overlap={tr.overlap}; max |param diff| {float(d.max()):.3e}; max update {float(upd.max()):.3e}; "
-          f"rel {float(d.norm() / upd.norm()):.3e}")
+    r0 = EnvGSRenderer(base, env, device=dev)
+    init = dict(r0.named_parameters())
+    ref = dict(r2.named_parameters())
+    worst = 0.0
+    for n in mine:
+        d = (mine[n] - ref[n]).norm()
+        upd = (ref[n] - init[n]).norm().clamp_min(1e-30)
+        worst = max(worst, float(d / upd))
+        print(f"  {n:16s} rel diff of the update {float(d / upd):.3e}")
+    print(f"world {world}: shard={tr.shard} overlap={tr.overlap} factored={tr.factored}; worst relative difference of a parameter update {worst:.3e}")
 dist.barrier()
 dist.destroy_process_group()
