@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: do not start the environment group's all-reduce from the gradient hook")
     ap.add_argument("--no-shard", action="store_true", help="N > 1: all-reduce + full-size Adam instead of reduce-scatter / sharded Adam / all-gather")
     ap.add_argument("--no-factored-sh", action="store_true", help="N > 1: exchange the base SH gradient itself instead of its rank-one factors")
+    ap.add_argument("--raster-sync", action="store_true",
+                    help="keep the reference's blocking read of the (tile, surfel) instance count in every rasterizer call "
+                         "(default: host-sync-free capacity mode after the first frame of a shape)")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip the in-process timing of the reference GPU operators")
     ap.add_argument("--reference-device", default="auto", choices=["auto", "cpu"],
                     help="--impl reference: 'auto' runs the real reference on the GPU when it can (else the CPU port); 'cpu' forces the CPU port")
@@ -295,7 +298,7 @@ def main():
         run_reference_arm(args)
         return
 
-    from envgs_b200 import _lib, scene
+    from envgs_b200 import _lib, rasterizer, scene
     from envgs_b200.dist import ViewParallelTrainer, init_process_group_from_env
     from envgs_b200.pipeline import EnvGSRenderer
     import torch.distributed as dist
@@ -305,6 +308,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     Pb, Pe, H, W = WORKLOADS[args.workload]
+    rasterizer.set_sync_free(not args.raster_sync)
     s0 = 0.005 * 1080 / H          # mean 3-sigma screen radius ~6 px at every resolution (s0 = 6 z / (3 f), f = 0.78 W)
 
     base = scene.make_base_set(Pb, seed=0, s0=s0)
@@ -395,10 +399,15 @@ def main():
         sampler.start()
     launches0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    step_events = []                                      # ENVGS_BENCH_STEP_TIMES=1: per-step device times (view-cost spread)
     barrier()
     ev0.record()
     for s in range(args.warmup, args.warmup + args.steps):
         resident_step(s)
+        if os.environ.get("ENVGS_BENCH_STEP_TIMES") == "1":
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            step_events.append(e)
     ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
@@ -416,6 +425,19 @@ def main():
     ev3.record()
     barrier()
     ms_e2e = ev2.elapsed_time(ev3)
+
+    if os.environ.get("ENVGS_BENCH_TORCH_PROFILE"):      # diagnostic: per-kernel device time of 6 steps on rank 0 (after the timed regions)
+        from torch.profiler import ProfilerActivity, profile
+        barrier()
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            for s in range(6):
+                resident_step(args.warmup + s)
+            barrier()
+        if rank == 0:
+            with open(os.environ["ENVGS_BENCH_TORCH_PROFILE"], "w") as f:
+                f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=70, max_name_column_width=90))
+            if os.environ.get("ENVGS_BENCH_TORCH_TRACE"):
+                prof.export_chrome_trace(os.environ["ENVGS_BENCH_TORCH_TRACE"])
 
     t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
@@ -520,7 +542,8 @@ def main():
         "config": {"workload": f"{args.workload}: {Pb} base + {Pe} env surfels, SH deg 3, {W}x{H}, {1 + TRACE_DEPTH.get(args.workload, 0)}-segment reflection trace, "
                                f"fwd+bwd + BVH rebuild + grad all-reduce + fused Adam, 1 view/rank/step",
                    "l2": "inputs_larger_than_L2 (surfel parameters 240+61 MB, maps 25-265 MB each vs 126 MB L2)",
-                   "parallelism": f"view-parallel x{world}"},
+                   "parallelism": f"view-parallel x{world}",
+                   "raster_host_sync": bool(args.raster_sync)},
         "e2e": {"value": round(e2e_value, 3), "unit": "Mpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": round(ms_e2e / args.steps, 4)},
         "gpu_launches": int(launches),
@@ -531,6 +554,9 @@ def main():
         "kernels_ms": kernels,
         "cpu_baseline": cpu,
     }
+    if step_events:
+        marks = [ev0] + step_events
+        line["step_ms"] = [round(marks[i].elapsed_time(marks[i + 1]), 4) for i in range(len(step_events))]
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -630,7 +656,18 @@ def time_reference_gpu_ops(renderer, cam, target, kernels_ms) -> dict:
 
 
 def renderer_last_num_rendered(renderer, cam) -> int:
-    """Instance count of one frame (what render_fwd streams): run the base pass once more and read it from autograd."""
+    """Instance count of one frame (what render_fwd streams): run the base pass once more and read it from autograd.  The
+    synchronous mode is forced for this call: in the sync-free mode the context holds the capacity, not the count."""
+    from envgs_b200 import rasterizer
+    was = dict(rasterizer._SYNC_FREE)
+    rasterizer.set_sync_free(False)
+    try:
+        return _last_num_rendered(renderer, cam)
+    finally:
+        rasterizer.set_sync_free(was["enabled"], was["margin"])
+
+
+def _last_num_rendered(renderer, cam) -> int:
     with torch.enable_grad():
         out = renderer.rasterize_base(cam)
         fn = out["render"].grad_fn

@@ -25,6 +25,7 @@ class RasterArgs(C.Structure):
         ("background", _fp), ("means3D", _fp), ("shs", _fp), ("colors_precomp", _fp), ("opacities", _fp),
         ("scales", _fp), ("rotations", _fp), ("transMat_precomp", _fp), ("viewmatrix", _fp), ("projmatrix", _fp),
         ("campos", _fp),
+        ("instance_capacity", C.c_int32), ("instance_count_out", _fp),
     ]
 
 

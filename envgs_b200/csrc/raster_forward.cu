@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(
 // binning
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) duplicate_kernel(int P, GeomState g, uint64_t* __restrict__ keys,
-                                                        uint32_t* __restrict__ vals, int gx) {
+                                                        uint32_t* __restrict__ vals, int gx, uint32_t cap) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= P) return;
     uint32_t n = g.tiles_touched[idx];
@@ -276,34 +276,50 @@ __global__ void __launch_bounds__(256) duplicate_kernel(int P, GeomState g, uint
         for (int x = tb.x; x < tb.z; x++) {
             uint64_t key = (uint64_t)(y * gx + x);
             key = (key << 32) | dbits;
-            keys[off] = key;
-            vals[off] = (uint32_t)idx;
+            if (off < cap) {       // sync-free mode: the buffer holds `cap` instances; anything beyond is dropped and flagged
+                keys[off] = key;
+                vals[off] = (uint32_t)idx;
+            }
             off++;
         }
 }
 
+// Sync-free mode: slots [count, cap) get the all-ones key (sorts behind every real instance) and the true count / overflow
+// flag are published for the caller.
+__global__ void __launch_bounds__(256) pad_keys_kernel(uint32_t cap, const uint32_t* __restrict__ count_ptr, uint64_t* __restrict__ keys,
+                                                       uint32_t* __restrict__ vals, int32_t* __restrict__ count_out) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n = *count_ptr;
+    if (idx == 0 && count_out) { count_out[0] = (int32_t)n; count_out[1] = n > cap ? 1 : 0; }
+    if (idx >= cap || idx < n) return;
+    keys[idx] = ~0ull;
+    vals[idx] = 0u;
+}
+
 __global__ void __launch_bounds__(256) tile_ranges_kernel(int L, const uint64_t* __restrict__ keys,
-                                                          uint2* __restrict__ ranges) {
+                                                          uint2* __restrict__ ranges, uint32_t n_tiles) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= L) return;
     uint32_t cur = (uint32_t)(keys[idx] >> 32);
-    if (idx == 0) ranges[cur].x = 0;
+    const bool cur_ok = cur < n_tiles;                  // padding entries of the sync-free mode carry tile id 0xffffffff
+    if (idx == 0) { if (cur_ok) ranges[cur].x = 0; }
     else {
         uint32_t prev = (uint32_t)(keys[idx - 1] >> 32);
-        if (cur != prev) { ranges[prev].y = idx; ranges[cur].x = idx; }
+        if (cur != prev) { if (prev < n_tiles) ranges[prev].y = idx; if (cur_ok) ranges[cur].x = idx; }
     }
-    if (idx == L - 1) ranges[cur].y = L;
+    if (idx == L - 1 && cur_ok) ranges[cur].y = L;
 }
 
 // Gather the per-instance render state into sorted structure-of-arrays order (BinningState::srec/sbox/sid/sfeat): one
 // 64-byte record gather + the feature row per instance, written back fully coalesced.  render_fwd and render_bwd then both
 // stream their tile's range with bulk asynchronous copies instead of each repeating the scattered gather.
 template <int C>
-__global__ void __launch_bounds__(256) gather_sorted_kernel(int N, const uint32_t* __restrict__ point_list,
+__global__ void __launch_bounds__(256) gather_sorted_kernel(int N, const uint32_t* __restrict__ count_ptr,
+                                                            const uint32_t* __restrict__ point_list,
                                                             const float4* __restrict__ rec, const short4* __restrict__ pixbox,
                                                             const float* __restrict__ features, BinningState b) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= N) return;
+    if (k >= N || (count_ptr && (uint32_t)k >= *count_ptr)) return;   // sync-free mode: N is the capacity, the real count is on the device
     const int id = (int)point_list[k];
 #pragma unroll
     for (int q = 0; q < 4; q++) b.srec[q][k] = rec[4 * (size_t)id + q];
@@ -539,9 +555,19 @@ static int raster_forward_impl(const envgs_raster_args& a, const envgs_raster_ou
         count_launch(2);
     }
 
+    const bool sync_free = a.instance_capacity > 0;
     int num_rendered = 0;
-    ENVGS_CUDA_TRY(cudaMemcpyAsync(&num_rendered, g.point_offsets + P - 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
-    ENVGS_CUDA_TRY(cudaStreamSynchronize(stream));
+    if (sync_free) {
+        num_rendered = a.instance_capacity;             // buffer size; the true count never leaves the device
+    } else {
+        ENVGS_CUDA_TRY(cudaMemcpyAsync(&num_rendered, g.point_offsets + P - 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        ENVGS_CUDA_TRY(cudaStreamSynchronize(stream));
+        if (a.instance_count_out) {
+            const int32_t two[2] = {num_rendered, 0};
+            ENVGS_CUDA_TRY(cudaMemcpyAsync(a.instance_count_out, two, sizeof(two), cudaMemcpyHostToDevice, stream));
+        }
+    }
+    const uint32_t* count_ptr = sync_free ? g.point_offsets + P - 1 : nullptr;
 
     size_t sort_bytes = sort_temp_bytes(num_rendered);
     size_t bin_bytes = BinningState::carve(nullptr, num_rendered, nullptr, sort_bytes, C);
@@ -554,8 +580,13 @@ static int raster_forward_impl(const envgs_raster_args& a, const envgs_raster_ou
     if (num_rendered > 0) {
         {
             ENVGS_TIMED("duplicate", stream);
-            duplicate_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, g, b.keys_unsorted, b.vals_unsorted, gx);
+            duplicate_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, g, b.keys_unsorted, b.vals_unsorted, gx, (uint32_t)num_rendered);
             ENVGS_LAUNCH_CHECK("duplicate", debug, stream);
+            if (sync_free) {
+                pad_keys_kernel<<<(num_rendered + 255) / 256, 256, 0, stream>>>((uint32_t)num_rendered, count_ptr, b.keys_unsorted, b.vals_unsorted,
+                                                                                a.instance_count_out);
+                ENVGS_LAUNCH_CHECK("pad_keys", debug, stream);
+            }
         }
         int bit = (int)higher_msb((uint32_t)(gx * gy));
         {
@@ -566,7 +597,7 @@ static int raster_forward_impl(const envgs_raster_args& a, const envgs_raster_ou
         }
         {
             ENVGS_TIMED("tile_ranges", stream);
-            tile_ranges_kernel<<<(num_rendered + 255) / 256, 256, 0, stream>>>(num_rendered, b.keys, im.ranges);
+            tile_ranges_kernel<<<(num_rendered + 255) / 256, 256, 0, stream>>>(num_rendered, b.keys, im.ranges, (uint32_t)(gx * gy));
             ENVGS_LAUNCH_CHECK("tile_ranges", debug, stream);
         }
     }
@@ -574,7 +605,7 @@ static int raster_forward_impl(const envgs_raster_args& a, const envgs_raster_ou
     const float* feat = a.colors_precomp ? a.colors_precomp : g.rgb;
     if (num_rendered > 0) {
         ENVGS_TIMED("gather_sorted", stream);
-        gather_sorted_kernel<C><<<(num_rendered + 255) / 256, 256, 0, stream>>>(num_rendered, b.point_list, g.rec, g.pixbox, feat, b);
+        gather_sorted_kernel<C><<<(num_rendered + 255) / 256, 256, 0, stream>>>(num_rendered, count_ptr, b.point_list, g.rec, g.pixbox, feat, b);
         ENVGS_LAUNCH_CHECK("gather_sorted", debug, stream);
     }
     {

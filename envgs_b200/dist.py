@@ -229,31 +229,36 @@ class ViewParallelTrainer:
         e0, e1 = self.flat.early_range
         f0, f1 = self.flat.factored_range
         sh_factored = False
+        sh_works, works = [], []
         if self.world > 1:
             self.flat.collect_stray_grads(0)             # every gradient home in the flat buffer (early group: no-op after the hook)
-            works = []
-            if self.factored:
+            if self.factored:                            # issued first: the SH update below only waits for these
                 sh_factored = gradsink.factor_written(self.renderer.shs)
                 if sh_factored:                          # 12 B per surfel and rank instead of 192 B both ways
-                    works.append(dist.all_gather_into_tensor(self._factors_all, self._factor_local, async_op=True))
-                    works.append(dist.all_gather_into_tensor(self._campos_all, self._campos_local, async_op=True))
+                    sh_works.append(dist.all_gather_into_tensor(self._factors_all, self._factor_local, async_op=True))
+                    sh_works.append(dist.all_gather_into_tensor(self._campos_all, self._campos_local, async_op=True))
                 else:                                    # the SH gradient arrived the ordinary way (no fused feature op in this graph)
-                    works.append(dist.all_reduce(self.flat.flat_grad[f0:f1], op=dist.ReduceOp.SUM, async_op=True))
+                    sh_works.append(dist.all_reduce(self.flat.flat_grad[f0:f1], op=dist.ReduceOp.SUM, async_op=True))
             if self._early_work is None and e1 > e0:     # no hook launch (overlap off): exchange the early group now
                 works.append(dist.all_reduce(self.flat.flat_grad[e0:e1], op=dist.ReduceOp.SUM, async_op=True))
             if self.shard:
                 works.append(dist.reduce_scatter_tensor(self._grad_shard, self.flat.flat_grad[l0:l1], op=dist.ReduceOp.SUM, async_op=True))
             elif l1 > l0:
                 works.append(dist.all_reduce(self.flat.flat_grad[l0:l1], op=dist.ReduceOp.SUM, async_op=True))
-            for w in works:
-                w.wait()
             if self._early_work is not None:
-                self._early_work.wait()
+                works.append(self._early_work)
+            if self.fused is None:                       # no fused optimizer: everything has to be home before the generic path
+                sh_works, works = [], sh_works + works
+                for w in works:
+                    w.wait()
+                works = []
         else:
             self.flat.collect_stray_grads()
         if self.fused is not None:
+            for w in sh_works:
+                w.wait()
             if self.fused_sh is not None:                # before the positions move: the basis is a function of (mean - campos)
-                if sh_factored:
+                if sh_factored:                          # runs while the base set's reduce-scatter is still on NCCL's stream
                     from . import _lib
                     shs, a = self.renderer.shs, self.fused_sh
                     a.t += 1
@@ -264,12 +269,16 @@ class ViewParallelTrainer:
                             a.betas[0], a.betas[1], a.eps, scale, torch.cuda.current_stream(shs.device).cuda_stream), "envgs_sh_adam_factored")
                 else:
                     self.fused_sh.step(grad_scale=scale, zero_grad=True)
+            for w in works:
+                w.wait()
             if self.shard:
                 self.fused.step(grad_scale=scale, zero_grad=False)
+                # in place: rank r's slice is already home.  The early group's update and the zero-fill run underneath it.
+                gather = dist.all_gather_into_tensor(self.flat.flat[l0:l1], self.flat.flat[self._shard_slice], async_op=True)
                 if self.fused_early is not None:
                     self.fused_early.step(grad_scale=scale, zero_grad=True)
-                dist.all_gather_into_tensor(self.flat.flat[l0:l1], self.flat.flat[self._shard_slice])   # in place: rank r's slice is already home
                 self.flat.flat_grad[l0:l1].zero_()
+                gather.wait()
             else:
                 self.fused.step(grad_scale=scale, zero_grad=True)
                 if self.fused_early is not None and self.factored:

@@ -6,6 +6,9 @@ libenvgs_b200.so and is reached through the C ABI (`envgs_raster_forward/backwar
 from __future__ import annotations
 
 import ctypes as C
+import math
+import os
+import warnings
 from typing import NamedTuple
 
 import torch
@@ -50,6 +53,55 @@ def reset_scratch_high_water_marks() -> None:
     """Forget the binning-buffer high-water marks (call after densify / prune shrank the set, or when switching to a much
     smaller resolution); the next frames re-learn them."""
     _ALLOC_HWM.clear()
+    _BUDGETS.clear()
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# Host-sync-free binning.  The reference blocks the host once per rasterizer call to read the (tile, surfel) instance count that
+# sizes the sort (rasterizer_impl.cu:283).  With the mode on, the first call for a given (device, H, W, C, P) still does that, and
+# every later one hands the library a capacity (`margin` x the largest count seen so far) instead: the count stays on the device,
+# is copied to pinned memory asynchronously and only looked at — without waiting — before a later call.  A frame whose count
+# exceeded the capacity lost its excess instances; that is reported with a warning and the budget grows.
+# ---------------------------------------------------------------------------------------------------------------------------------
+_SYNC_FREE = {"enabled": os.environ.get("ENVGS_RASTER_SYNC_FREE", "0") == "1", "margin": 1.3}
+_CAP_QUANTUM = 1 << 16
+_BUDGETS: dict = {}
+
+
+def set_sync_free(enabled: bool, margin: float = 1.3) -> None:
+    _SYNC_FREE["enabled"] = bool(enabled)
+    _SYNC_FREE["margin"] = float(margin)
+    _BUDGETS.clear()
+
+
+class _InstanceBudget:
+    def __init__(self):
+        self.max_seen = -1
+        self.pending = []     # (pinned int32[2], event)
+        self.overflows = 0
+
+    def poll(self):
+        while self.pending and self.pending[0][1].query():
+            host, _ = self.pending.pop(0)
+            count, over = int(host[0]), int(host[1])
+            if over:
+                self.overflows += 1
+                warnings.warn(f"rasterizer: a frame produced {count} (tile, surfel) instances, more than the sync-free capacity; "
+                              "the excess was dropped from that frame and the capacity grows", RuntimeWarning)
+            self.max_seen = max(self.max_seen, count)
+
+    def capacity(self):
+        if self.max_seen < 0:
+            return 0
+        want = max(int(math.ceil(self.max_seen * _SYNC_FREE["margin"])), 1)
+        return (want + _CAP_QUANTUM - 1) // _CAP_QUANTUM * _CAP_QUANTUM
+
+    def watch(self, count_dev):
+        host = torch.empty(2, dtype=torch.int32, pin_memory=True)
+        host.copy_(count_dev, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(count_dev.device))
+        self.pending.append((host, ev))
 
 
 
@@ -170,6 +222,14 @@ def make_module(C_channels: int):
             scratch = _Scratch(device, (H, W, C_channels))
 
             args = _make_args(C_channels, s, bg, m3, shc, col, opa, sc, rot, cov, vm, pm, cam)
+            budget, count_dev = None, None
+            if _SYNC_FREE["enabled"] and P > 0:
+                budget = _BUDGETS.setdefault((str(device), H, W, C_channels, P), _InstanceBudget())
+                budget.poll()
+                args.instance_capacity = budget.capacity()
+                if args.instance_capacity:
+                    count_dev = torch.empty(2, dtype=torch.int32, device=device)
+                    args.instance_count_out = _lib.ptr(count_dev)
             out = _lib.RasterOut(_lib.ptr(color), _lib.ptr(others), _lib.ptr(weight), _lib.ptr(radii))
             stream = torch.cuda.current_stream(device).cuda_stream
 
@@ -192,6 +252,12 @@ def make_module(C_channels: int):
                     raise ex
             else:
                 num_rendered = run()
+            if budget is not None:
+                if count_dev is None:
+                    budget.max_seen = max(budget.max_seen, int(num_rendered))   # the synchronous first frame
+                else:
+                    with torch.cuda.device(device):
+                        budget.watch(count_dev)
 
             ctx.raster_settings = s
             ctx.num_rendered = num_rendered

@@ -9,7 +9,7 @@
  * passed as void*.  No torch types cross this boundary.  Functions return 0 (or a non-negative count) on
  * success and a negative code on failure; envgs_last_error() then holds a message.  Nothing here
  * synchronises the stream except the 4-byte read-back of the instance count in envgs_raster_forward
- * (the reference does the same: rasterizer_impl.cu:283).
+ * (the reference does the same: rasterizer_impl.cu:283) — and not even that with envgs_raster_args.instance_capacity set.
  *
  * Reference interfaces replaced (paths relative to /root/reference/submodules):
  *   envgs_raster_forward   <- RasterizeGaussiansCUDA            diff-surfel-rasterizations/diff-surfel-rasterization-wet-ch05/rasterize_points.cu:39-136
@@ -69,6 +69,13 @@ typedef struct envgs_raster_args {
     const float* viewmatrix;       /* (4,4) W2C^T, contiguous        */
     const float* projmatrix;       /* (4,4) (Proj*W2C)^T, contiguous */
     const float* campos;           /* (3,)           */
+    /* Host-sync-free mode (0 / NULL = off).  With instance_capacity > 0 the forward call sizes the binning buffer for that many
+     * (tile, surfel) instances, never reads the true count back (the reference blocks on it, rasterizer_impl.cu:283) and
+     * returns instance_capacity — the value to hand to envgs_raster_backward as num_rendered.  The true count and an overflow
+     * flag (count > capacity: the excess instances were dropped from this frame) are written to instance_count_out[0..1]
+     * (device int32) for the caller to inspect later, e.g. after an asynchronous copy. */
+    int32_t instance_capacity;
+    int32_t* instance_count_out;
 } envgs_raster_args;
 
 typedef struct envgs_raster_out {

@@ -193,3 +193,46 @@ def test_fused_glue_matches_pytorch_pipeline(built_lib):
     for n in res[False][2]:
         t = Hh.trimmed_rel_l2(res[True][2][n], res[False][2][n])
         assert t < 2e-3, f"{n}: {t:.3e} (full {Hh.rel_l2(res[True][2][n], res[False][2][n]):.3e})"
+
+
+def test_sync_free_binning_is_bit_identical_and_flags_overflow(built_lib, monkeypatch):
+    """Host-sync-free mode (include/envgs_b200.h `instance_capacity`): after the first (synchronous) frame the count stays on
+    the device; images and gradients must equal the synchronous path bit for bit, and a frame that exceeds the capacity is
+    reported, not crashed on."""
+    import warnings
+    from envgs_b200 import rasterizer as R
+    R.set_sync_free(False)
+    monkeypatch.setattr(R, "_CAP_QUANTUM", 256)
+    base = scene.make_base_set(6000, seed=21, s0=0.03)
+    cams = scene.ring_cameras(4, 96, 128, seed=5)
+    g_color, g_others = Hh.upstream((3, 96, 128), 3), Hh.upstream((7, 96, 128), 4, 0.1)
+    feats = [Hh.base_features(base, c, 3) for c in cams]
+    want = [Hh.run_cuda_raster(base, c, 3, feats=f, g_color=g_color, g_others=g_others) for c, f in zip(cams, feats)]
+    try:
+        R.set_sync_free(True, margin=1.5)
+        for rep in range(2):
+            for c, f, w in zip(cams, feats, want):
+                got = Hh.run_cuda_raster(base, c, 3, feats=f, g_color=g_color, g_others=g_others)
+                for k in w:      # forward outputs bit-equal; gradients are float-atomic sums, equal up to their ordering noise
+                    if k.startswith("g_") or k == "weight":
+                        assert Hh.rel_l2(got[k], w[k]) < 1e-5, (rep, k)
+                    else:
+                        assert torch.equal(got[k], w[k]), (rep, k)
+        torch.cuda.synchronize()
+        budget = next(iter(R._BUDGETS.values()))
+        budget.poll()
+        assert budget.max_seen > 0 and budget.overflows == 0 and not budget.pending
+        # force an overflow: pretend far fewer instances were ever seen
+        budget.max_seen = 1000
+        got = Hh.run_cuda_raster(base, cams[0], 3, feats=feats[0], g_color=g_color, g_others=g_others)
+        torch.cuda.synchronize()
+        with warnings.catch_warnings(record=True) as rec:
+            warnings.simplefilter("always")
+            budget.poll()
+        assert budget.overflows == 1 and any("sync-free capacity" in str(r.message) for r in rec)
+        assert torch.isfinite(got["color"]).all() and torch.isfinite(got["g_means"]).all()
+        # and it recovers: the next frame has the grown budget and is exact again
+        got = Hh.run_cuda_raster(base, cams[0], 3, feats=feats[0], g_color=g_color, g_others=g_others)
+        assert torch.equal(got["color"], want[0]["color"])
+    finally:
+        R.set_sync_free(False)
