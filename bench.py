@@ -49,9 +49,9 @@ def parse_args():
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: do not start the environment group's all-reduce from the gradient hook")
     ap.add_argument("--no-shard", action="store_true", help="N > 1: all-reduce + full-size Adam instead of reduce-scatter / sharded Adam / all-gather")
     ap.add_argument("--no-factored-sh", action="store_true", help="N > 1: exchange the base SH gradient itself instead of its rank-one factors")
-    ap.add_argument("--raster-sync", action="store_true",
-                    help="keep the reference's blocking read of the (tile, surfel) instance count in every rasterizer call "
-                         "(default: host-sync-free capacity mode after the first frame of a shape)")
+    ap.add_argument("--raster-sync-free", action="store_true",
+                    help="rasterizer without the reference's blocking read of the (tile, surfel) instance count (capacity mode after the "
+                         "first frame of a shape; measured: no gain on this GPU-bound step, see DESIGN.md section 8b)")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip the in-process timing of the reference GPU operators")
     ap.add_argument("--reference-device", default="auto", choices=["auto", "cpu"],
                     help="--impl reference: 'auto' runs the real reference on the GPU when it can (else the CPU port); 'cpu' forces the CPU port")
@@ -308,7 +308,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     Pb, Pe, H, W = WORKLOADS[args.workload]
-    rasterizer.set_sync_free(not args.raster_sync)
+    rasterizer.set_sync_free(args.raster_sync_free)
     s0 = 0.005 * 1080 / H          # mean 3-sigma screen radius ~6 px at every resolution (s0 = 6 z / (3 f), f = 0.78 W)
 
     base = scene.make_base_set(Pb, seed=0, s0=s0)
@@ -512,8 +512,9 @@ def main():
         if rooflines:
             roofline = dict(max(rooflines, key=lambda r: r["launch_ms"]))      # the dominant kernel group of the step
             roofline.update(num_rendered=N, visible_surfels=P_v, rays=R, composited_hits=Hh, env_surfels_hit=P_hit,
-                            note="every group is fp32-issue / latency bound, not HBM bound (SURVEY.md §8d; DESIGN.md §6): traffic <= "
-                                 "algorithmic bytes, so there are no wasted re-reads to remove")
+                            note="every group is fp32-issue / latency bound, not HBM bound (SURVEY.md §8d; DESIGN.md §6): measured DRAM "
+                                 "traffic is below the algorithmic bytes except for render_bwd (1.55x: read-modify-write of the gradient "
+                                 "rows its REDs touch), at 4 % of the HBM peak either way")
 
         # ---- the UNMODIFIED reference operators on the same inputs, same process (oracle/ref_ops.py) ----
         if world == 1 and not args.no_ref_gpu:
@@ -543,7 +544,7 @@ def main():
                                f"fwd+bwd + BVH rebuild + grad all-reduce + fused Adam, 1 view/rank/step",
                    "l2": "inputs_larger_than_L2 (surfel parameters 240+61 MB, maps 25-265 MB each vs 126 MB L2)",
                    "parallelism": f"view-parallel x{world}",
-                   "raster_host_sync": bool(args.raster_sync)},
+                   "raster_host_sync": not args.raster_sync_free},
         "e2e": {"value": round(e2e_value, 3), "unit": "Mpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": round(ms_e2e / args.steps, 4)},
         "gpu_launches": int(launches),

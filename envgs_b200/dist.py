@@ -175,7 +175,12 @@ class ViewParallelTrainer:
             shs = renderer.shs
             P, M = shs.shape[0], shs.shape[1]
             self._factor_local = torch.zeros(P, 3, dtype=torch.float32, device=dev)
-            self._factors_all = torch.zeros(self.world, P, 3, dtype=torch.float32, device=dev)
+            # The factor all-gather is the largest exposed collective (12 B x P x N received per rank) and the SH update that consumes
+            # it is the largest optimizer kernel: split both into surfel chunks, so chunk k's update runs under chunk k+1's gather.
+            n_chunks = max(1, int(os.environ.get("ENVGS_SH_EXCHANGE_CHUNKS", 4 if P >= (1 << 18) else 1)))
+            per = -(-P // n_chunks)
+            self._sh_chunks = [(a, min(a + per, P)) for a in range(0, P, per)]
+            self._factors_all = [torch.zeros(self.world, b - a, 3, dtype=torch.float32, device=dev) for a, b in self._sh_chunks]
             self._campos_local = torch.zeros(3, dtype=torch.float32, device=dev)
             self._campos_all = torch.zeros(self.world, 3, dtype=torch.float32, device=dev)
             self.fused_sh = FlatAdam(self.flat.flat[f0:f1], self.flat.flat_grad[f0:f1], lr=lr)   # owns the SH moments and step count
@@ -235,8 +240,9 @@ class ViewParallelTrainer:
             if self.factored:                            # issued first: the SH update below only waits for these
                 sh_factored = gradsink.factor_written(self.renderer.shs)
                 if sh_factored:                          # 12 B per surfel and rank instead of 192 B both ways
-                    sh_works.append(dist.all_gather_into_tensor(self._factors_all, self._factor_local, async_op=True))
                     sh_works.append(dist.all_gather_into_tensor(self._campos_all, self._campos_local, async_op=True))
+                    for (a, b), buf in zip(self._sh_chunks, self._factors_all):
+                        sh_works.append(dist.all_gather_into_tensor(buf, self._factor_local[a:b], async_op=True))
                 else:                                    # the SH gradient arrived the ordinary way (no fused feature op in this graph)
                     sh_works.append(dist.all_reduce(self.flat.flat_grad[f0:f1], op=dist.ReduceOp.SUM, async_op=True))
             if self._early_work is None and e1 > e0:     # no hook launch (overlap off): exchange the early group now
@@ -255,20 +261,29 @@ class ViewParallelTrainer:
         else:
             self.flat.collect_stray_grads()
         if self.fused is not None:
-            for w in sh_works:
-                w.wait()
             if self.fused_sh is not None:                # before the positions move: the basis is a function of (mean - campos)
-                if sh_factored:                          # runs while the base set's reduce-scatter is still on NCCL's stream
+                if sh_factored:                          # runs while the later chunks and the base set's reduce-scatter are still on NCCL's stream
                     from . import _lib
                     shs, a = self.renderer.shs, self.fused_sh
                     a.t += 1
+                    row = shs.shape[1] * 3
+                    flat_sh = self.flat.flat[f0:f1]
+                    sh_works[0].wait()
                     with torch.cuda.device(shs.device):
-                        _lib.check(_lib.lib().envgs_sh_adam_factored(
-                            shs.shape[0], 3, shs.shape[1], self.world, _lib.ptr(self.renderer.means), _lib.ptr(self._campos_all),
-                            _lib.ptr(self._factors_all), _lib.ptr(self.flat.flat[f0:f1]), _lib.ptr(a.exp_avg), _lib.ptr(a.exp_avg_sq), a.t, a.lr,
-                            a.betas[0], a.betas[1], a.eps, scale, torch.cuda.current_stream(shs.device).cuda_stream), "envgs_sh_adam_factored")
+                        for (c0, c1), buf, w in zip(self._sh_chunks, self._factors_all, sh_works[1:]):
+                            w.wait()
+                            _lib.check(_lib.lib().envgs_sh_adam_factored(
+                                c1 - c0, 3, shs.shape[1], self.world, _lib.ptr(self.renderer.means[c0:c1]), _lib.ptr(self._campos_all),
+                                _lib.ptr(buf), _lib.ptr(flat_sh[c0 * row:c1 * row]), _lib.ptr(a.exp_avg[c0 * row:c1 * row]),
+                                _lib.ptr(a.exp_avg_sq[c0 * row:c1 * row]), a.t, a.lr, a.betas[0], a.betas[1], a.eps, scale,
+                                torch.cuda.current_stream(shs.device).cuda_stream), "envgs_sh_adam_factored")
                 else:
+                    for w in sh_works:
+                        w.wait()
                     self.fused_sh.step(grad_scale=scale, zero_grad=True)
+            else:
+                for w in sh_works:
+                    w.wait()
             for w in works:
                 w.wait()
             if self.shard:

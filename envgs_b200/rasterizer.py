@@ -75,15 +75,20 @@ def set_sync_free(enabled: bool, margin: float = 1.3) -> None:
 
 
 class _InstanceBudget:
+    SLOTS = 32   # pinned read-back slots, reused round-robin: no host allocation (cudaHostAlloc synchronises) on the step path
+
     def __init__(self):
         self.max_seen = -1
-        self.pending = []     # (pinned int32[2], event)
+        self.host = None
+        self.events = [None] * self.SLOTS
+        self.pending = []     # slot indices in issue order
+        self.head = 0
         self.overflows = 0
 
     def poll(self):
-        while self.pending and self.pending[0][1].query():
-            host, _ = self.pending.pop(0)
-            count, over = int(host[0]), int(host[1])
+        while self.pending and self.events[self.pending[0]].query():
+            slot = self.pending.pop(0)
+            count, over = int(self.host[slot, 0]), int(self.host[slot, 1])
             if over:
                 self.overflows += 1
                 warnings.warn(f"rasterizer: a frame produced {count} (tile, surfel) instances, more than the sync-free capacity; "
@@ -97,12 +102,17 @@ class _InstanceBudget:
         return (want + _CAP_QUANTUM - 1) // _CAP_QUANTUM * _CAP_QUANTUM
 
     def watch(self, count_dev):
-        host = torch.empty(2, dtype=torch.int32, pin_memory=True)
-        host.copy_(count_dev, non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(count_dev.device))
-        self.pending.append((host, ev))
-
+        if self.host is None:
+            self.host = torch.zeros(self.SLOTS, 2, dtype=torch.int32).pin_memory()
+        slot = self.head
+        if slot in self.pending:          # the host is a full ring ahead of the device: this frame's count goes unobserved
+            return
+        self.head = (slot + 1) % self.SLOTS
+        self.host[slot].copy_(count_dev, non_blocking=True)
+        if self.events[slot] is None:
+            self.events[slot] = torch.cuda.Event()
+        self.events[slot].record(torch.cuda.current_stream(count_dev.device))
+        self.pending.append(slot)
 
 
 class _Scratch:
