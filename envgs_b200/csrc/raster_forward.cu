@@ -562,6 +562,10 @@ static int raster_forward_impl(const envgs_raster_args& a, const envgs_raster_ou
     } else {
         ENVGS_CUDA_TRY(cudaMemcpyAsync(&num_rendered, g.point_offsets + P - 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
         ENVGS_CUDA_TRY(cudaStreamSynchronize(stream));
+        if (num_rendered < 0) {   // the inclusive sum is a uint32: more than INT_MAX instances would read back as an error code
+            set_error("%u (tile, surfel) instances exceed the 2^31 - 1 this interface can return", (unsigned)num_rendered);
+            return ENVGS_ERR_INVALID;
+        }
         if (a.instance_count_out) {
             const int32_t two[2] = {num_rendered, 0};
             ENVGS_CUDA_TRY(cudaMemcpyAsync(a.instance_count_out, two, sizeof(two), cudaMemcpyHostToDevice, stream));

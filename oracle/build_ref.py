@@ -28,6 +28,7 @@ OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 VARIANTS = {
     "ref_rast_wet": "diff-surfel-rasterization-wet",            # NUM_CHANNELS 3, in-kernel SH
     "ref_rast_wet_ch05": "diff-surfel-rasterization-wet-ch05",  # NUM_CHANNELS 5 (what EnvGS imports)
+    "ref_rast_wet_ch07": "diff-surfel-rasterization-wet-ch07",  # NUM_CHANNELS 7 (render() picks it for 7-channel features)
 }
 
 

@@ -1,5 +1,5 @@
 """GPU parity at BASELINE.json's own sizes, live against the UNMODIFIED reference built for sm_100a under oracle/_ref
-(oracle/build_ref.py): the reference rasterizer extensions (`ref_rast_wet`, `ref_rast_wet_ch05`) and the reference tracer
+(oracle/build_ref.py): the reference rasterizer extensions (`ref_rast_wet`, `ref_rast_wet_ch05`, `ref_rast_wet_ch07`) and the reference tracer
 device programs behind the OptiX emulation header.  Both sides run in this process on identical tensors.
 
 Tolerances are the north star's, unmodified: 1e-4 on every rendered value, 1e-3 on the FULL relative L2 norm of every
@@ -48,6 +48,7 @@ def _ref_raster(mod_name, base, cam, C, feats, use_sh, gc, go, bg):
     (500_000, 5, False, "ref_rast_wet_ch05"),    # BASELINE config 2, as EnvGS runs it (torch SH -> 5 precomputed channels)
     (500_000, 3, True, "ref_rast_wet"),          # BASELINE config 2, in-kernel SH
     (1_000_000, 5, False, "ref_rast_wet_ch05"),  # BASELINE config 3, rasterizer half
+    (250_000, 7, False, "ref_rast_wet_ch07"),    # the 7-channel variant render() can pick (gaussian2d_utils.py:1013-1015)
 ])
 def test_rasterizer_matches_reference_at_baseline_sizes(built_lib, P, C, use_sh, mod):
     _need(os.path.join(mod, mod + ".so"))
@@ -56,7 +57,7 @@ def test_rasterizer_matches_reference_at_baseline_sizes(built_lib, P, C, use_sh,
     cam = scene.ring_cameras(1, H, W, seed=2)[0]
     feats = None if use_sh else Hh.base_features(base, cam, C)
     gc, go = Hh.upstream((C, H, W), 3, 1e-3), Hh.upstream((7, H, W), 4, 1e-3)
-    bg = torch.tensor([0.1, 0.2, 0.3, 0.0, 0.0])[:C].contiguous()
+    bg = torch.tensor([0.1, 0.2, 0.3, 0.0, 0.0, 0.0, 0.0])[:C].contiguous()
     ref = _ref_raster(mod, base, cam, C, feats, use_sh, gc, go, bg)
     cu = Hh.run_cuda_raster(base, cam, C, feats=feats, use_sh=use_sh, g_color=gc, g_others=go, bg=bg)
     assert torch.equal(cu["radii"], ref["radii"]), f"{int((cu['radii'] != ref['radii']).sum())} radii differ"
