@@ -12,6 +12,7 @@ Prints ONE JSON line on rank 0.
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import math
 import os
@@ -232,12 +233,15 @@ def run_reference_arm_gpu(args) -> bool:
     for k in range(args.warmup):
         step(k)
     torch.cuda.synchronize()
+    gc.collect()
+    gc.disable()                                          # same host-side policy as the main arm: no cyclic GC pass inside the timed region
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for k in range(args.warmup, args.warmup + args.steps):
         step(k)
     e1.record()
     torch.cuda.synchronize()
+    gc.enable()
     ms = e0.elapsed_time(e1) / args.steps
     v = H * W / (ms * 1e-3) / 1e6
     from oracle import ref_trace as RT
@@ -392,6 +396,10 @@ def main():
     for s in range(args.warmup):
         resident_step(s)
     barrier()
+    # Manual GC (as large training loops do): one collection here, none inside the timed regions — a generation-2 pass of the cyclic
+    # collector is a multi-millisecond host stall that lands on a random step.
+    gc.collect()
+    gc.disable()
 
     # ---- timed region 1: inputs resident in HBM ----
     sampler = ClockSampler(local)
@@ -425,6 +433,7 @@ def main():
     ev3.record()
     barrier()
     ms_e2e = ev2.elapsed_time(ev3)
+    gc.enable()
 
     if os.environ.get("ENVGS_BENCH_TORCH_PROFILE"):      # diagnostic: per-kernel device time of 6 steps on rank 0 (after the timed regions)
         from torch.profiler import ProfilerActivity, profile
@@ -544,7 +553,7 @@ def main():
                                f"fwd+bwd + BVH rebuild + grad all-reduce + fused Adam, 1 view/rank/step",
                    "l2": "inputs_larger_than_L2 (surfel parameters 240+61 MB, maps 25-265 MB each vs 126 MB L2)",
                    "parallelism": f"view-parallel x{world}",
-                   "raster_host_sync": not args.raster_sync_free},
+                   "raster_host_sync": not args.raster_sync_free, "host_gc": "one collection before the timed regions, cyclic GC off inside (both arms)"},
         "e2e": {"value": round(e2e_value, 3), "unit": "Mpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": round(ms_e2e / args.steps, 4)},
         "gpu_launches": int(launches),

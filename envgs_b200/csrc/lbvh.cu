@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(256) collapse4_kernel(int n_internal, const Bv
 // The Karras LBVH splits purely by Morton prefix; its sibling boxes overlap and a ray visits ~2x the nodes an
 // SAH-quality tree needs (round-1 verdict).  PLOC builds bottom-up instead: every cluster looks at its 2r neighbours in
 // Morton order, picks the one whose union box has the smallest surface area, and mutually-nearest pairs merge; repeat until
-// one cluster is left.  ~35 iterations of 4 small kernels for 256 K surfels (~1 ms), which is why lbvh_build re-uses the
+// one cluster is left.  ~35 iterations of 4 small kernels for 256 K surfels, which is why lbvh_build re-uses the
 // topology for several calls and only refits in between (boxes always come from the current quads, so any valid topology
 // gives exactly the same hits).
 constexpr int PLOC_RADIUS = 8;
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(256) ploc_init_kernel(int P, const uint32_t* _
                                                         const float4* __restrict__ leaf_hi, float4* __restrict__ lo, float4* __restrict__ hi,
                                                         int* __restrict__ link, int* __restrict__ slot, int* __restrict__ counter) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k == 0) { counter[0] = 0; counter[1] = P; }
+    if (k == 0) { counter[0] = 0; counter[1] = P; counter[2] = P; }
     if (k >= P) return;
     const uint32_t sid = vals_sorted[k];
     lo[k] = leaf_lo[sid];
@@ -320,8 +320,12 @@ __global__ void __launch_bounds__(256) ploc_init_kernel(int P, const uint32_t* _
     slot[k] = P - 1 + k;
 }
 
-__global__ void __launch_bounds__(256) ploc_nn_kernel(int n, const float4* __restrict__ lo, const float4* __restrict__ hi, int* __restrict__ nn) {
+// The cluster count of an iteration lives on the device (`n_ptr`, ping-pong between counter[1] and counter[2]); the host only knows an
+// upper bound (the count it last read back) and sizes the grids with it, so several iterations run between two read-backs.
+__global__ void __launch_bounds__(256) ploc_nn_kernel(const int* __restrict__ n_ptr, const float4* __restrict__ lo, const float4* __restrict__ hi,
+                                                      int* __restrict__ nn) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = *n_ptr;
     if (i >= n) return;
     const float4 l4 = lo[i], h4 = hi[i];
     const float3 l = f3(l4.x, l4.y, l4.z), h = f3(h4.x, h4.y, h4.z);
@@ -337,11 +341,16 @@ __global__ void __launch_bounds__(256) ploc_nn_kernel(int n, const float4* __res
     nn[i] = bj;
 }
 
-__global__ void __launch_bounds__(256) ploc_merge_kernel(int n, int P, const int* __restrict__ nn, float4* __restrict__ lo, float4* __restrict__ hi,
+__global__ void __launch_bounds__(256) ploc_merge_kernel(const int* __restrict__ n_ptr, int n_bound, int P, const int* __restrict__ nn,
+                                                         float4* __restrict__ lo, float4* __restrict__ hi,
                                                          int* __restrict__ link, int* __restrict__ slot, int* __restrict__ valid,
                                                          BvhNode* __restrict__ nodes, int* __restrict__ parent, int* __restrict__ counter) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const int n = *n_ptr;
+    if (i >= n) {
+        if (i < n_bound) valid[i] = 0;      // the scan runs over the host's bound
+        return;
+    }
     const int j = nn[i];
     if (j < 0 || nn[j] != i) { valid[i] = 1; return; }
     if (i > j) { valid[i] = 0; return; }
@@ -359,40 +368,49 @@ __global__ void __launch_bounds__(256) ploc_merge_kernel(int n, int P, const int
     if (id == 0) parent[0] = -1;
 }
 
-__global__ void __launch_bounds__(256) ploc_compact_kernel(int n, const int* __restrict__ valid, const int* __restrict__ scan,
+__global__ void __launch_bounds__(256) ploc_compact_kernel(const int* __restrict__ n_ptr, const int* __restrict__ valid, const int* __restrict__ scan,
                                                            const float4* __restrict__ lo, const float4* __restrict__ hi,
                                                            const int* __restrict__ link, const int* __restrict__ slot,
                                                            float4* __restrict__ lo2, float4* __restrict__ hi2, int* __restrict__ link2,
-                                                           int* __restrict__ slot2, int* __restrict__ counter) {
+                                                           int* __restrict__ slot2, int* __restrict__ n_next) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = *n_ptr;
     if (i >= n) return;
     if (valid[i]) {
         const int d = scan[i];
         lo2[d] = lo[i]; hi2[d] = hi[i]; link2[d] = link[i]; slot2[d] = slot[i];
     }
-    if (i == n - 1) counter[1] = scan[i] + valid[i];
+    if (i == n - 1) *n_next = scan[i] + valid[i];
 }
 
 static int ploc_topology(Lbvh& t, int P, cudaStream_t stream) {
     ploc_init_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, t.vals_sorted, (const float4*)t.leaf_lo, (const float4*)t.leaf_hi, t.cl_lo[0],
                                                          t.cl_hi[0], t.cl_link[0], t.cl_slot[0], t.cl_counter);
     ENVGS_LAUNCH_CHECK("ploc_init", false, stream);
-    int n = P, cur = 0;
-    for (int iter = 0; n > 1 && iter < 4096; iter++) {
+    // Iterations run in batches of PLOC_BATCH between two 4-byte read-backs of the cluster count: the kernels take the count from the
+    // device, the grids are sized with the count at the start of the batch.  A single cluster is a fixed point (no neighbour, no
+    // merge), so the surplus iterations of the last batch change nothing.  This build runs once every few calls, not in the per-step path.
+    constexpr int PLOC_BATCH = 4;
+    int n = P, cur = 0, iter = 0;
+    while (n > 1 && iter < 4096) {
         const int blocks = (n + 255) / 256;
-        ploc_nn_kernel<<<blocks, 256, 0, stream>>>(n, t.cl_lo[cur], t.cl_hi[cur], t.cl_nn);
-        ploc_merge_kernel<<<blocks, 256, 0, stream>>>(n, P, t.cl_nn, t.cl_lo[cur], t.cl_hi[cur], t.cl_link[cur], t.cl_slot[cur], t.cl_valid,
-                                                     t.nodes, t.parent, t.cl_counter);
-        ENVGS_CUDA_TRY(cub::DeviceScan::ExclusiveSum(t.scan_temp, t.scan_temp_bytes, t.cl_valid, t.cl_scan, n, stream));
-        ploc_compact_kernel<<<blocks, 256, 0, stream>>>(n, t.cl_valid, t.cl_scan, t.cl_lo[cur], t.cl_hi[cur], t.cl_link[cur], t.cl_slot[cur],
-                                                       t.cl_lo[cur ^ 1], t.cl_hi[cur ^ 1], t.cl_link[cur ^ 1], t.cl_slot[cur ^ 1], t.cl_counter);
-        count_launch(5);
-        int alive = 0;   // one 4-byte read-back per iteration: this build runs once every few calls, not in the per-step path
-        ENVGS_CUDA_TRY(cudaMemcpyAsync(&alive, t.cl_counter + 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        for (int b = 0; b < PLOC_BATCH; b++, iter++) {
+            const int* n_ptr = t.cl_counter + 1 + (iter & 1);
+            int* n_next = t.cl_counter + 1 + ((iter + 1) & 1);
+            ploc_nn_kernel<<<blocks, 256, 0, stream>>>(n_ptr, t.cl_lo[cur], t.cl_hi[cur], t.cl_nn);
+            ploc_merge_kernel<<<blocks, 256, 0, stream>>>(n_ptr, n, P, t.cl_nn, t.cl_lo[cur], t.cl_hi[cur], t.cl_link[cur], t.cl_slot[cur], t.cl_valid,
+                                                         t.nodes, t.parent, t.cl_counter);
+            ENVGS_CUDA_TRY(cub::DeviceScan::ExclusiveSum(t.scan_temp, t.scan_temp_bytes, t.cl_valid, t.cl_scan, n, stream));
+            ploc_compact_kernel<<<blocks, 256, 0, stream>>>(n_ptr, t.cl_valid, t.cl_scan, t.cl_lo[cur], t.cl_hi[cur], t.cl_link[cur], t.cl_slot[cur],
+                                                           t.cl_lo[cur ^ 1], t.cl_hi[cur ^ 1], t.cl_link[cur ^ 1], t.cl_slot[cur ^ 1], n_next);
+            count_launch(5);
+            cur ^= 1;
+        }
+        int alive = 0;
+        ENVGS_CUDA_TRY(cudaMemcpyAsync(&alive, t.cl_counter + 1 + (iter & 1), sizeof(int), cudaMemcpyDeviceToHost, stream));
         ENVGS_CUDA_TRY(cudaStreamSynchronize(stream));
         if (alive >= n || alive < 1) { set_error("PLOC made no progress (%d -> %d clusters)", n, alive); return ENVGS_ERR_STATE; }
         n = alive;
-        cur ^= 1;
     }
     if (n != 1) { set_error("PLOC did not converge"); return ENVGS_ERR_STATE; }
     return ENVGS_OK;

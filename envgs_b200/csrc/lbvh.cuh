@@ -64,7 +64,7 @@ struct Lbvh {
     int* cl_nn = nullptr;
     int* cl_valid = nullptr;
     int* cl_scan = nullptr;
-    int* cl_counter = nullptr;               // [0] merges done so far, [1] clusters alive after compaction
+    int* cl_counter = nullptr;               // [0] merges done so far, [1] and [2] clusters alive (ping-pong between iterations)
     char* scan_temp = nullptr;
     size_t scan_temp_bytes = 0;
     int full_builds = 0, calls_since_full = 1 << 30;   // topology-reuse policy (lbvh_build)

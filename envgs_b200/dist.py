@@ -1,10 +1,12 @@
 """View-parallel training step: one process per GPU, every rank holds a replica of both surfel sets and renders its own
-view(s); gradients are summed with ONE NCCL all-reduce over a single flat fp32 buffer.
+view(s); gradients are summed over NCCL in three groups of ONE flat fp32 buffer: the
+environment set from a gradient hook underneath the rasterizer's backward, the base SH gradient as rank-one factors, the rest
+of the base set as reduce-scatter -> 1/N-sharded fused Adam -> in-place all-gather.
 
 The reference has no usable multi-GPU path for EnvGS (its DDP wrapper breaks when densification re-creates parameters,
 SURVEY.md §2.4), so this is new host logic: parameters are views into one flat tensor and their `.grad`s are views into one
-flat gradient tensor, which the backward kernels' outputs accumulate into — no gather copy before the collective.
-Works with backend `nccl` (GPU) and `gloo` (CPU tests, world_size 2).
+flat gradient tensor, which the backward kernels write into directly (gradsink.py) — no gather copy before a collective.
+Works with backend `nccl` (GPU) and `gloo` (CPU tests, world_size 2: one all-reduce per group, torch Adam).
 """
 from __future__ import annotations
 
