@@ -384,13 +384,15 @@ def main():
             return pack_dev, tgt
 
     feed = HostFeed()
+    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
 
     def e2e_step(step):
         pack_dev, tgt = feed.get(step)
         feed.issue(step + 1)
         cam = cam_from_pack(view_of(step), pack_dev)
-        loss = trainer.step(cam, tgt)
-        return loss.to("cpu", non_blocking=False)          # D2H read of the step's result
+        trainer.step(cam, tgt, loss_out=loss_host)
+        trainer.loss_ready.synchronize()                   # D2H read of the step's result: the copy is queued right behind the loss kernel,
+        return float(loss_host)                            # so the host waits for the forward pass only and goes on queueing the next step
 
     # ---- warm-up ----
     for s in range(args.warmup):

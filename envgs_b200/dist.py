@@ -162,6 +162,7 @@ class ViewParallelTrainer:
         self.opt = None
         self.fused = self.fused_early = None
         self._grad_is_zero = False
+        self.loss_ready = None
         self._early_work = None
         self._early_seen = 0
         cuda = self.flat.flat.is_cuda
@@ -223,12 +224,20 @@ class ViewParallelTrainer:
                     self._early_work = dist.all_reduce(self.flat.flat_grad[e0:e1], op=dist.ReduceOp.SUM, async_op=True)
         return hook
 
-    def step(self, cam, target) -> torch.Tensor:
+    def step(self, cam, target, loss_out: torch.Tensor | None = None) -> torch.Tensor:
+        """`loss_out` (pinned host tensor, optional): the loss is copied into it as soon as the forward pass has produced it and
+        `self.loss_ready` (a CUDA event) marks the copy — a caller that logs the loss every step waits on that event instead of
+        on the whole step, so the host keeps queueing the next step while the backward pass and the update still run."""
         if not self._grad_is_zero:                       # the fused update leaves the gradient buffer zeroed for the next step
             self.flat.zero_grad()
         self._early_seen, self._early_work = 0, None
         out = self.renderer(cam, target)
         loss = self.renderer.loss(out, target)
+        if loss_out is not None:
+            loss_out.copy_(loss.detach().reshape(loss_out.shape), non_blocking=True)
+            if self.loss_ready is None:
+                self.loss_ready = torch.cuda.Event()
+            self.loss_ready.record()
         self.flat.begin_backward()
         loss.backward()
         scale = 1.0 / self.world if (self.world > 1 and self.average) else 1.0
