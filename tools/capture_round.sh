@@ -9,9 +9,11 @@ python bench.py --impl reference --steps 5 --warmup 3 > gpurun_out/bench_ref_$TA
 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-profile --no-ref-gpu > gpurun_out/launches_$TAG.log 2>&1
+if [ -z "$SKIP_NCU_FULL" ]; then
 ncu --set full --clock-control none --import-source on \
     -k regex:"render_fwd|render_bwd|traverse_kernel|shade_fwd_kernel|shade_bwd_kernel|gather_sorted" -s 8 -c 16 \
     -o gpurun_out/prof_$TAG -f python tools/prof_step.py config3 3 > gpurun_out/ncu_$TAG.log 2>&1
+fi
 timeout 600 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_raster.py -q -x -k "ragged or empty or sync_free or precomputed_colors" 2>&1 | tail -6 > gpurun_out/sanitizer_$TAG.log
 timeout 600 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_trace.py -q -x -k "two_segment or degenerate or fast_path" 2>&1 | tail -6 >> gpurun_out/sanitizer_$TAG.log
 ls -la gpurun_out | tail -12
