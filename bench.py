@@ -510,6 +510,8 @@ def main():
                                        bytes=24 * R + (52 + 64 * 1) * R + (44 + 12 * S) * Hh)
             groups["trace_bwd"] = dict(kernel="shade_bwd_kernel (+ overflow fallback)", kernels=["trace_shade_bwd", "trace_bwd_fallback"],
                                        bytes=(24 + 52 + 64 * 1 + 44 + 24) * R + (40 + 12 * S) * Hh + (40 + 12 * S) * P_hit)
+            # the dominant single kernel on its own (24 B of ray in, one 128-byte hit line out per ray)
+            groups["traverse"] = dict(kernel="traverse_kernel (alone; part of trace_fwd)", kernels=["trace_traverse"], bytes=(24 + 128) * R)
         rooflines = []
         for name, gdef in groups.items():
             t_ms = sum(kernels.get(k, 0.0) for k in gdef["kernels"])
@@ -521,7 +523,9 @@ def main():
                               "frac": round(ach / peak, 4), "traffic": tj.get("traffic"), "traffic_source": tj.get("source"),
                               "peak_source": peak_src, "algorithmic_bytes": int(gdef["bytes"]), "launch_ms": round(t_ms, 4)})
         if rooflines:
-            roofline = dict(max(rooflines, key=lambda r: r["launch_ms"]))      # the dominant kernel group of the step
+            # the dominant stage of the step in SURVEY.md section 8(d)'s decomposition (trace_fwd = traversal + shading: its
+            # per-unit byte figure covers both kernels); the traversal kernel alone is the `traverse` entry of `rooflines`
+            roofline = dict(max(rooflines, key=lambda r: r["launch_ms"]))
             roofline.update(num_rendered=N, visible_surfels=P_v, rays=R, composited_hits=Hh, env_surfels_hit=P_hit,
                             note="every group is fp32-issue / latency bound, not HBM bound (SURVEY.md §8d; DESIGN.md §6): measured DRAM "
                                  "traffic is below the algorithmic bytes except for render_bwd (1.55x: read-modify-write of the gradient "
