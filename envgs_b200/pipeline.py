@@ -11,6 +11,7 @@ rank.  All map-sized glue stays PyTorch, exactly as in the reference (the drop-i
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 
 import torch
@@ -89,6 +90,9 @@ class EnvGSRenderer(nn.Module):
         self.fused_features = fused_features   # False: evaluate the base SH colours in PyTorch exactly like the reference
         self.fused_glue = fused_glue           # False: per-pixel glue (reflection, dpt2norm, blend, loss) in PyTorch like the reference
         self.lambda_normal = 0.04
+        # fused path: build / refit the environment set's acceleration structure on a side stream underneath the rasterizer forward
+        self.async_bvh = os.environ.get("ENVGS_ASYNC_BVH", "1") != "0"
+        self._env_stream = None
         dev = torch.device(device)
         P = lambda t: nn.Parameter(t.to(dev).contiguous())
         self.means, self.scales, self.rotations, self.opacities = P(base.means), P(base.scales), P(base.rotations), P(base.opacities)
@@ -132,13 +136,38 @@ class EnvGSRenderer(nn.Module):
                     surf_normal=surf_normal, dist=allmap[6:7], radii=radii, weight=weight, means2D=means2D, image=image, allmap=allmap)
 
     # ---- environment pass ------------------------------------------------------------------------------------
-    def trace_env(self, cam: scene.Camera, ref_o: torch.Tensor, ref_d: torch.Tensor) -> dict:
+    def _prepare_env(self) -> torch.Tensor:
+        """Quad corners of the traced set + acceleration structure over them: every training iteration (optix_utils.py:71-85)."""
         with torch.no_grad():
             if self.fused_glue:
                 v, f = glue.quad_vertices(self.env_means, self.env_scales, self.env_rotations)
             else:
                 v, f = scene.quad_vertices(self.env_means, self.env_scales, self.env_rotations)
-            self.tracer.build_acceleration_structure(v, f, rebuild=True)   # every training iteration (optix_utils.py:71-85)
+            self.tracer.build_acceleration_structure(v, f, rebuild=True)
+        return v
+
+    def _prepare_env_async(self, step_start: torch.cuda.Event):
+        """The same on a side stream: it depends on the environment parameters only, so it can run underneath the base set's
+        rasterizer forward (and the host-side read-backs of a full topology rebuild no longer stall the main stream's queue).
+        `step_start` orders it behind everything the main stream did before this step (the previous update of the parameters)."""
+        dev = self.env_means.device
+        if self._env_stream is None:
+            self._env_stream = torch.cuda.Stream(dev)
+        main = torch.cuda.current_stream(dev)
+        with torch.cuda.stream(self._env_stream):
+            self._env_stream.wait_event(step_start)
+            v = self._prepare_env()
+            done = torch.cuda.Event()
+            done.record(self._env_stream)
+        v.record_stream(main)
+        return v, done
+
+    def trace_env(self, cam: scene.Camera, ref_o: torch.Tensor, ref_d: torch.Tensor, prepared=None) -> dict:
+        if prepared is None:
+            v = self._prepare_env()
+        else:
+            v, done = prepared
+            torch.cuda.current_stream(v.device).wait_event(done)
         s = SurfelTracingSettings(cam.H, cam.W, cam.tanfovx, cam.tanfovy, self.env_bg, 1.0, cam.viewmatrix, cam.projmatrix, 3,
                                   cam.campos, False, False, self.max_trace_depth, self.specular_threshold if self.max_trace_depth else 0.0)
         grads3D = torch.zeros_like(self.env_means, requires_grad=True)
@@ -188,11 +217,16 @@ class EnvGSRenderer(nn.Module):
 
     def _forward_fused(self, cam: scene.Camera, target: torch.Tensor) -> dict:
         """Same computation with the per-pixel glue in two fused kernels per direction (envgs_b200/glue.py)."""
+        overlap = self.has_env and self.async_bvh and self.means.is_cuda
+        if overlap:
+            step_start = torch.cuda.Event()
+            step_start.record()
         image, radii, allmap, weight, means2D = self._raster(cam)
         env = None
         if self.has_env:
+            prepared = self._prepare_env_async(step_start) if overlap else None   # queued after the rasterizer forward on the host side
             ref_o, ref_d = glue.reflect_rays(allmap, cam)
-            env = self.trace_env(cam, ref_o, ref_d)
+            env = self.trace_env(cam, ref_o, ref_d, prepared)
         rgb, loss, parts = glue.blend_loss(image, allmap, None if env is None else env["rgb"], target, cam, self.lambda_normal)
         out = dict(rgb=rgb, loss=loss, loss_parts=parts, radii=radii, weight=weight, means2D=means2D, image=image, allmap=allmap)
         if env is not None:
