@@ -84,3 +84,45 @@ def test_product_path_never_imports_the_oracle():
     for d in ("diff_surfel_rasterization_wet", "diff_surfel_rasterization_wet_ch05", "diff_surfel_rasterization_wet_ch07", "diff_surfel_tracing"):
         src = open(os.path.join(ROOT, d, "__init__.py")).read()
         assert "oracle" not in src
+
+
+def _header_structs():
+    """struct name -> [(kind, field name)] parsed from include/envgs_b200.h; kind is 'ptr', 'i32', 'f32' or 'u64'."""
+    import re
+    text = open(os.path.join(ROOT, "include", "envgs_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    out = {}
+    for m in re.finditer(r"typedef struct (\w+) \{(.*?)\} \1;", text, flags=re.S):
+        fields = []
+        for decl in m.group(2).split(";"):
+            decl = " ".join(decl.split())
+            if not decl:
+                continue
+            base, names = decl.rsplit(" ", 1)[0], decl
+            # "const float* a, *b" does not occur in this header; lists are plain "int32_t P, C, sh_degree"
+            typ = decl[:decl.index(decl.split(",")[0].split()[-1])].strip()
+            for name in decl[len(typ):].split(","):
+                name = name.strip()
+                ptr = "*" in typ or name.startswith("*")
+                kind = "ptr" if ptr else {"int32_t": "i32", "uint32_t": "i32", "float": "f32", "uint64_t": "u64", "size_t": "u64"}[typ.replace("const ", "")]
+                fields.append((kind, name.lstrip("*")))
+        out[m.group(1)] = fields
+    return out
+
+
+def test_ctypes_structures_mirror_the_header():
+    """The Python shim passes these structs by reference: a field added to the header but not to envgs_b200/_lib.py (or the other way
+    round, or in another order) would silently shift every later member."""
+    import ctypes as C
+    from envgs_b200 import _lib
+    pairs = {"envgs_raster_args": _lib.RasterArgs, "envgs_raster_out": _lib.RasterOut, "envgs_raster_grads": _lib.RasterGrads,
+             "envgs_trace_args": _lib.TraceArgs, "envgs_trace_out": _lib.TraceOut, "envgs_trace_grads": _lib.TraceGrads,
+             "envgs_glue_camera": _lib.GlueCamera, "envgs_densify_params": _lib.DensifyParams, "envgs_row_array": _lib.RowArray}
+    structs = _header_structs()
+    kind_of = {C.c_void_p: "ptr", C.c_int32: "i32", C.c_int: "i32", C.c_uint32: "i32", C.c_float: "f32", C.c_uint64: "u64", C.c_size_t: "u64"}
+    for cname, cls in pairs.items():
+        assert cname in structs, cname
+        want = structs[cname]
+        got = [(kind_of.get(t, "ptr" if hasattr(t, "contents") or t is C.c_char_p else str(t)), n) for n, t in cls._fields_]
+        assert [n for _, n in got] == [n for _, n in want], f"{cname}: field names/order differ:\n  header {want}\n  ctypes {got}"
+        assert [k for k, _ in got] == [k for k, _ in want], f"{cname}: field kinds differ:\n  header {want}\n  ctypes {got}"
