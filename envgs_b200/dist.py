@@ -235,9 +235,10 @@ class ViewParallelTrainer:
         loss = self.renderer.loss(out, target)
         if loss_out is not None:
             loss_out.copy_(loss.detach().reshape(loss_out.shape), non_blocking=True)
-            if self.loss_ready is None:
-                self.loss_ready = torch.cuda.Event()
-            self.loss_ready.record()
+            if loss.is_cuda:
+                if self.loss_ready is None:
+                    self.loss_ready = torch.cuda.Event()
+                self.loss_ready.record()
         self.flat.begin_backward()
         loss.backward()
         scale = 1.0 / self.world if (self.world > 1 and self.average) else 1.0

@@ -156,6 +156,56 @@ def test_view_parallel_gradient_allreduce_gloo_world2(overlap):
             assert torch.allclose(torch.tensor(grads[n]), expect[n], rtol=1e-5, atol=1e-5), n
 
 
+def _worker_adam(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from envgs_b200.dist import ViewParallelTrainer, init_process_group_from_env
+    init_process_group_from_env("gloo")
+    r = _ToyRenderer()
+    tr = ViewParallelTrainer(r, lr=1e-2, average=True, optimizer=True)
+    loss_host = torch.zeros(())
+    losses = []
+    for step in range(3):
+        cam = torch.full((7, 3), float(rank + 1 + step))
+        tr.step(cam, torch.tensor(0.5), loss_out=loss_host)
+        losses.append(float(loss_host))
+    q.put((rank, {n: p.detach().tolist() for n, p in r.named_parameters()}, losses))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_view_parallel_optimizer_step_gloo_world2():
+    """Three optimisation steps on two ranks (gloo, CPU: one all-reduce per group + torch Adam over the flat buffer): the replicas end
+    bit-identical and equal a single process that averages the two views' gradients and runs torch.optim.Adam; `loss_out` receives
+    each step's loss."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29950 + os.getpid() % 40
+    procs = [ctx.Process(target=_worker_adam, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+    ref = _ToyRenderer()
+    opt = torch.optim.Adam(ref.parameters(), lr=1e-2, eps=1e-15)
+    want_losses = {0: [], 1: []}
+    for step in range(3):
+        opt.zero_grad()
+        for rank in range(2):
+            cam = torch.full((7, 3), float(rank + 1 + step))
+            loss = ref.loss(ref(cam), torch.tensor(0.5))
+            want_losses[rank].append(float(loss.detach()))
+            (loss / 2).backward()
+        opt.step()
+    for n, p in ref.named_parameters():
+        assert res[0][1][n] == res[1][1][n], n                       # replicas bit-identical
+        assert torch.allclose(torch.tensor(res[0][1][n]), p.detach(), rtol=1e-5, atol=1e-6), n
+    for rank in range(2):
+        assert res[rank][2] == pytest.approx(want_losses[rank], rel=1e-5)
+
+
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` without a GPU (the CPU oracle port) prints one JSON line with the keys the driver reads and never
     touches CUDA."""
