@@ -119,3 +119,58 @@ def test_trace_reference_atomics_noise_is_below_tolerance():
     for name in MG.TRACE_CASES:
         gold = torch.load(os.path.join(GOLD, name + ".pt"))
         assert gold.get("noise_g_means") is None or gold["noise_g_means"] < 1e-5
+
+
+# ---- densify / prune / split: the PyTorch twin the device implementation is compared with (tests/test_gpu_densify.py) against the
+# ---- UNMODIFIED reference code run on CPU (oracle/make_densify_golden.py -> tests/golden/densify_ref_*.pt)
+from oracle import make_densify_golden as MDG  # noqa: E402
+
+
+@pytest.mark.parametrize("name", list(MDG.CASES))
+def test_densify_twin_matches_reference_golden(name):
+    from tests.densify_twin import NAMES, TwinModel
+    gold = torch.load(os.path.join(GOLD, name + ".pt"), weights_only=False)
+    params, moments, stats, noise, screen, prune_vis = MDG.case_inputs(name)
+    assert MDG.input_checksum(params, moments, stats, noise) == pytest.approx(gold["input_checksum"], rel=1e-12)
+    tw = TwinModel({n: params[n].clone() for n in NAMES}, {k: v.clone() for k, v in stats.items()}, noise)
+    for n in NAMES:
+        p = getattr(tw, n)
+        tw.optimizer.state[p] = {"step": torch.tensor(5.0), "exp_avg": moments[n][0].clone(), "exp_avg_sq": moments[n][1].clone()}
+    r = gold["rules"]
+    with torch.no_grad():
+        tw.densify_and_prune(r["min_opacity"], r["min_gradient"], r["densify_grad_threshold"], r["densify_size_threshold"],
+                             split_screen_threshold=r["split_screen_threshold"], prune_visibility=r["prune_visibility"], n_after=r["n_after"])
+    out = gold["outputs"]
+    assert tw._xyz.shape[0] == out["params"]["_xyz"].shape[0] and tw._xyz.shape[0] != params["_xyz"].shape[0]
+    assert torch.equal(tw.src, out["src"]) and torch.equal(tw.is_clone, out["is_clone"])      # same rows survive, in the same order
+    assert int(out["is_clone"].sum()) > 0 and int((out["src"].bincount() > 1).sum()) > 0      # clones and split children are present
+    for n in NAMES:
+        got, want = getattr(tw, n).detach(), out["params"][n]
+        assert torch.allclose(got, want, rtol=1e-6, atol=1e-7), (n, float((got - want).abs().max()))
+        m, v = tw.moments(n)
+        assert torch.equal(m, out["exp_avg"][n]) and torch.equal(v, out["exp_avg_sq"][n]), n   # optimizer surgery: copies and zeros
+    # statistics just before the reference's final reset_stats (the twin leaves the reset to its caller)
+    for k, want in out["stats_before_reset"].items():
+        got = getattr(tw, k).reshape(-1)
+        assert torch.allclose(got, want, rtol=1e-6, atol=0), k
+
+
+def test_host_side_restatements_match_reference_golden():
+    """camera feed, depth -> normal and the degree-3 SH evaluation (the PyTorch twins of the fused kernels) against outputs of the
+    reference's own functions (oracle/make_host_golden.py -> tests/golden/host_ref.pt)."""
+    from oracle import make_host_golden as MH
+    from envgs_b200 import gaussian_io as IO
+    from envgs_b200 import pipeline as PL
+    gold = torch.load(os.path.join(GOLD, "host_ref.pt"), weights_only=False)
+    cam, depth, shs, xyz = MH.inputs()
+    c = IO.camera_from_batch(dict(K=cam.K[None], R=cam.R[None], T=cam.T[None], H=MH.H, W=MH.W, n=cam.znear, f=cam.zfar))
+    g = gold["camera"]
+    assert torch.allclose(c.viewmatrix, g["world_view_transform"], rtol=0, atol=1e-7)
+    assert torch.allclose(c.projmatrix, g["full_proj_transform"], rtol=1e-6, atol=1e-6)
+    assert torch.allclose(c.campos, g["camera_center"], rtol=0, atol=1e-6)
+    assert c.tanfovx == pytest.approx(g["tanfovx"], rel=1e-7) and c.tanfovy == pytest.approx(g["tanfovy"], rel=1e-7)
+    nrm = PL.depth_to_normal(c, depth)
+    assert torch.allclose(nrm, gold["dpt2norm"], rtol=0, atol=2e-5), float((nrm - gold["dpt2norm"]).abs().max())
+    dirs = torch.nn.functional.normalize(xyz - c.campos[None], dim=-1)
+    rgb = PL.eval_sh_deg3(shs, dirs)
+    assert torch.allclose(rgb, gold["eval_sh_deg3"], rtol=1e-5, atol=1e-6), float((rgb - gold["eval_sh_deg3"]).abs().max())
