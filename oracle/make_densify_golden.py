@@ -42,7 +42,7 @@ CASES = {
 RULES = dict(min_opacity=0.05, min_gradient=2e-5, densify_grad_threshold=2e-4, densify_size_threshold=0.02)
 
 
-def load_reference_module(ref_file: str = REF_FILE, mod_name: str = "ref_gaussian2d_utils"):
+def load_reference_module(ref_file: str = REF_FILE, mod_name: str = "ref_gaussian2d_utils", extra_stubs: dict | None = None):
     class dotdict(dict):
         __getattr__ = dict.get
         __setattr__ = dict.__setitem__
@@ -65,6 +65,7 @@ def load_reference_module(ref_file: str = REF_FILE, mod_name: str = "ref_gaussia
     pkg.__path__, utils.__path__ = [], []
     stubs = {"easyvolcap": pkg, "easyvolcap.utils": utils, "easyvolcap.utils.console_utils": console,
              "easyvolcap.utils.net_utils": net, "easyvolcap.utils.sh_utils": sh, "plyfile": ply}
+    stubs.update(extra_stubs or {})
     saved = {k: sys.modules.get(k) for k in stubs}
     sys.modules.update(stubs)
     try:

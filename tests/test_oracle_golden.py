@@ -161,6 +161,7 @@ def test_host_side_restatements_match_reference_golden():
     from oracle import make_host_golden as MH
     from envgs_b200 import gaussian_io as IO
     from envgs_b200 import pipeline as PL
+    from envgs_b200 import scene
     gold = torch.load(os.path.join(GOLD, "host_ref.pt"), weights_only=False)
     cam, depth, shs, xyz = MH.inputs()
     c = IO.camera_from_batch(dict(K=cam.K[None], R=cam.R[None], T=cam.T[None], H=MH.H, W=MH.W, n=cam.znear, f=cam.zfar))
@@ -174,3 +175,7 @@ def test_host_side_restatements_match_reference_golden():
     dirs = torch.nn.functional.normalize(xyz - c.campos[None], dim=-1)
     rgb = PL.eval_sh_deg3(shs, dirs)
     assert torch.allclose(rgb, gold["eval_sh_deg3"], rtol=1e-5, atol=1e-6), float((rgb - gold["eval_sh_deg3"]).abs().max())
+    env = MH.disk_inputs()
+    v, f = scene.quad_vertices(env.means, env.scales, env.rotations)                 # HardwareRendering.get_disks: 4 corners + 2 triangles per surfel
+    assert torch.allclose(v, gold["get_disks"]["v"], rtol=1e-5, atol=1e-6), float((v - gold["get_disks"]["v"]).abs().max())
+    assert torch.equal(f.int(), gold["get_disks"]["f"])
