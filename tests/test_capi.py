@@ -126,3 +126,38 @@ def test_ctypes_structures_mirror_the_header():
         got = [(kind_of.get(t, "ptr" if hasattr(t, "contents") or t is C.c_char_p else str(t)), n) for n, t in cls._fields_]
         assert [n for _, n in got] == [n for _, n in want], f"{cname}: field names/order differ:\n  header {want}\n  ctypes {got}"
         assert [k for k, _ in got] == [k for k, _ in want], f"{cname}: field kinds differ:\n  header {want}\n  ctypes {got}"
+
+
+def test_drop_in_packages_match_the_reference_api_surface(built_lib):
+    """Names, argument order, defaults, NamedTuple fields and the wrappers' own exception messages of the four reference packages
+    (extracted from their sources by oracle/make_api_golden.py -> tests/golden/api_surface.json) against the drop-in packages."""
+    import importlib
+    import inspect
+    import json
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "api_surface.json")))
+    for pkg, ref in gold.items():
+        mod = importlib.import_module(pkg)
+        for fname, f in ref["functions"].items():
+            fn = getattr(mod, fname)
+            params = list(inspect.signature(fn).parameters)
+            assert params == f["args"], (pkg, fname, params, f["args"])
+        for cname, c in ref["classes"].items():
+            cls = getattr(mod, cname)
+            if "NamedTuple" in c["bases"]:
+                assert list(cls._fields) == c["fields"], (pkg, cname)
+                continue
+            for mname, m in c["methods"].items():
+                meth = getattr(cls, mname)
+                sig = inspect.signature(meth)
+                params = list(sig.parameters)
+                want = m["args"]
+                if m["staticmethod"] is False and params and params[0] != "self" and want and want[0] == "self":
+                    want = want[1:]                      # bound-style introspection of functions defined without `self`
+                assert params == want, (pkg, cname, mname, params, want)
+                for arg, default in m["defaults"].items():
+                    got = sig.parameters[arg].default
+                    assert got == default or (got is None and default is None), (pkg, cname, mname, arg, got, default)
+        # the messages of the exceptions the reference wrappers raise themselves appear verbatim in the drop-in sources
+        src = open(os.path.join(ROOT, "envgs_b200", "rasterizer.py" if "rasterization" in pkg else "tracer.py")).read()
+        for exc, msg in ref["raises"]:
+            assert msg in src, (pkg, exc, msg)
