@@ -66,9 +66,24 @@ def surface(path: str) -> dict:
     return out
 
 
+HOST_SOURCES = {   # the C++ entry points' own argument checks (AT_ERROR -> RuntimeError in Python)
+    "rasterizer": f"{RAST}/diff-surfel-rasterization-wet-ch05/rasterize_points.cu",
+    "tracer": "/root/reference/submodules/diff-surfel-tracing/trace_surfels.cpp",
+}
+
+
+def host_errors(path: str) -> list:
+    import re
+    return sorted(set(re.findall(r'AT_ERROR\("([^"]+)"\)', open(path).read())))
+
+
 if __name__ == "__main__":
     res = {name: surface(path) for name, path in SOURCES.items()}
+    res["_host_errors"] = {k: host_errors(v) for k, v in HOST_SOURCES.items()}
     with open(os.path.join(ROOT, "tests", "golden", "api_surface.json"), "w") as f:
         json.dump(res, f, indent=1, sort_keys=True)
+    print(res["_host_errors"])
     for name, s in res.items():
+        if name.startswith("_"):
+            continue
         print(name, "functions", list(s["functions"]), "classes", {k: list(v["methods"]) for k, v in s["classes"].items()}, "raises", len(s["raises"]))

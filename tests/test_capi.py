@@ -135,6 +135,9 @@ def test_drop_in_packages_match_the_reference_api_surface(built_lib):
     import inspect
     import json
     gold = json.load(open(os.path.join(ROOT, "tests", "golden", "api_surface.json")))
+    for which, msgs in gold.pop("_host_errors").items():     # AT_ERROR checks of the C++ entry points: same RuntimeError messages
+        src = open(os.path.join(ROOT, "envgs_b200", which + ".py")).read()
+        assert msgs and all(f'RuntimeError("{m}")' in src for m in msgs), (which, msgs)
     for pkg, ref in gold.items():
         mod = importlib.import_module(pkg)
         for fname, f in ref["functions"].items():
