@@ -77,8 +77,32 @@ def host_errors(path: str) -> list:
     return sorted(set(re.findall(r'AT_ERROR\("([^"]+)"\)', open(path).read())))
 
 
+CONST_SOURCES = [f"{RAST}/diff-surfel-rasterization-wet-ch05/cuda_rasterizer/config.h",
+                 f"{RAST}/diff-surfel-rasterization-wet-ch05/cuda_rasterizer/auxiliary.h",
+                 "/root/reference/submodules/diff-surfel-tracing/optix_tracer/config.h"]
+
+
+def constants() -> dict:
+    """Numeric `#define NAME value` and `__device__ const float NAME = value;` of the reference's configuration headers (the
+    rasterizer's NUM_CHANNELS is per variant and left out; the tracer's is kept as TRACER_NUM_CHANNELS)."""
+    import re
+    out = {}
+    for path in CONST_SOURCES:
+        text = open(path).read()
+        pairs = re.findall(r"^#define\s+(\w+)\s+([-+0-9.eE]+)f?\s*(?://.*)?$", text, flags=re.M)
+        pairs += re.findall(r"^__device__ const float (\w+) = ([-+0-9.eE]+)f?;", text, flags=re.M)
+        for name, val in pairs:
+            if name == "NUM_CHANNELS":
+                if "optix_tracer" not in path:
+                    continue
+                name = "TRACER_NUM_CHANNELS"
+            out[name] = float(val)
+    return out
+
+
 if __name__ == "__main__":
     res = {name: surface(path) for name, path in SOURCES.items()}
+    res["_constants"] = constants()
     res["_host_errors"] = {k: host_errors(v) for k, v in HOST_SOURCES.items()}
     with open(os.path.join(ROOT, "tests", "golden", "api_surface.json"), "w") as f:
         json.dump(res, f, indent=1, sort_keys=True)

@@ -128,6 +128,30 @@ def test_ctypes_structures_mirror_the_header():
         assert [k for k, _ in got] == [k for k, _ in want], f"{cname}: field kinds differ:\n  header {want}\n  ctypes {got}"
 
 
+def _check_constants(ref: dict):
+    """The reference's configuration constants (config.h / auxiliary.h of the rasterizer, config.h of the tracer) against the
+    constexpr block of envgs_b200/csrc/common.cuh and the module constants of envgs_b200/tracer.py."""
+    import re
+    from envgs_b200 import tracer
+    text = open(os.path.join(ROOT, "envgs_b200", "csrc", "common.cuh")).read()
+    mine = {}
+    for line in re.findall(r"^constexpr (?:int|float) ([^;]+);", text, flags=re.M):
+        for name, val in re.findall(r"(\w+) = ([-+0-9.eE]+)f?(?=\s*(?:,|$))", line):
+            mine[name] = float(val)
+    mapping = {"BLOCK_X": "TILE_X", "BLOCK_Y": "TILE_Y", "near_n": "NEAR_N", "far_n": "FAR_N", "FilterSize": "FILTER_SIZE",
+               "FilterInvSquare": "FILTER_INV_SQUARE", "DEPTH_OFFSET": "DEPTH_OFFSET", "ALPHA_OFFSET": "ALPHA_OFFSET",
+               "NORMAL_OFFSET": "NORMAL_OFFSET", "MIDDEPTH_OFFSET": "MIDDEPTH_OFFSET", "DISTORTION_OFFSET": "DISTORTION_OFFSET",
+               "CHUNK_SIZE": "TR_CHUNK", "MAX_INTERSECTION": "TR_MAX_INTERSECTION", "MID_CHANNELS": "TR_MID_CHANNELS",
+               "MAX_TRACE_DEPTH": "TR_MAX_TRACE_DEPTH", "START_OFFSET": "TR_START_OFFSET", "STEP_EPSILON": "TR_STEP_EPSILON",
+               "DEPTH_INFINTY": "TR_DEPTH_INF", "RAYO_MID_OFFSET": "MID_RAYO", "RAYD_MID_OFFSET": "MID_RAYD", "DPT_MID_OFFSET": "MID_DPT",
+               "ACC_MID_OFFSET": "MID_ACC", "NORM_MID_OFFSET": "MID_NORM", "AUX_MID_OFFSET": "MID_AUX", "RGB_MID_OFFSET": "MID_RGB"}
+    for r, m in mapping.items():
+        assert r in ref and m in mine, (r, m)
+        assert mine[m] == pytest.approx(ref[r], rel=1e-6), (r, ref[r], m, mine[m])
+    assert (tracer.NUM_CHANNELS, tracer.AUX_CHANNELS, tracer.MID_CHANNELS, tracer.MAX_TRACE_DEPTH) == \
+        (ref["TRACER_NUM_CHANNELS"], ref["AUX_CHANNELS"], ref["MID_CHANNELS"], ref["MAX_TRACE_DEPTH"])
+
+
 def test_drop_in_packages_match_the_reference_api_surface(built_lib):
     """Names, argument order, defaults, NamedTuple fields and the wrappers' own exception messages of the four reference packages
     (extracted from their sources by oracle/make_api_golden.py -> tests/golden/api_surface.json) against the drop-in packages."""
@@ -135,6 +159,8 @@ def test_drop_in_packages_match_the_reference_api_surface(built_lib):
     import inspect
     import json
     gold = json.load(open(os.path.join(ROOT, "tests", "golden", "api_surface.json")))
+    consts = gold.pop("_constants")
+    _check_constants(consts)
     for which, msgs in gold.pop("_host_errors").items():     # AT_ERROR checks of the C++ entry points: same RuntimeError messages
         src = open(os.path.join(ROOT, "envgs_b200", which + ".py")).read()
         assert msgs and all(f'RuntimeError("{m}")' in src for m in msgs), (which, msgs)
